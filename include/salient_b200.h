@@ -1,0 +1,225 @@
+/*
+ * salient_b200.h -- C ABI of libsalient_b200.so: the B200 (sm_100a) mini-batch generation
+ * path of SALIENT++ (neighbour sampling -> dedup/relabel -> partition-book translation ->
+ * VIP-cache split -> feature gather -> peer-to-peer miss fetch).
+ *
+ * This is the drop-in boundary.  The reference exposes the same operations as a pybind11
+ * module with torch::Tensor arguments (fast_sampler/fast_sampler.cpp:1280-1396); here every
+ * entry point takes plain device pointers, sizes and a CUDA stream, so any host language can
+ * bind it (INTEGRATION.md shows the ctypes and the pybind/libtorch stubs).  There is no CPU
+ * fallback anywhere behind this interface.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all functions are asynchronous with respect to the host unless stated otherwise;
+ *   - return value: 0 on success, otherwise a cudaError_t (>0) or an SPP_E* code (<0);
+ *     spp_last_error() returns a message for the calling thread;
+ *   - node ids are < 2^31 (the reference narrows to int32 too, fast_sampler.cpp:196-199).
+ */
+#ifndef SALIENT_B200_H_
+#define SALIENT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPP_ABI_VERSION 1
+#define SPP_MAX_PARTS 16   /* partitions in a RangePartitionBook                               */
+#define SPP_MAX_HOPS 8     /* hops per mini-batch                                              */
+#define SPP_MAX_FANOUT 128 /* without-replacement fanout per hop (full neighbourhood: no cap)  */
+
+#define SPP_EINVAL (-1)      /* bad argument                                                   */
+#define SPP_ECAPACITY (-2)   /* a caller-provided buffer is too small (host-detectable cases)  */
+#define SPP_EUNSUPPORTED (-3)
+
+/* meta block written by the sampler (int64 each, device memory, SPP_META_WORDS long) */
+#define SPP_META_WORDS 32
+#define SPP_META_NODES(h) (h)       /* [0..L]: |n_id| before hop h; [L] = final N_b (h = hop)   */
+#define SPP_META_EDGES(h) (12 + (h)) /* [12..12+L): edges kept by hop h                         */
+#define SPP_META_OVERFLOW 24        /* !=0: a buffer bound was exceeded on the device           */
+
+int spp_abi_version(void);
+const char* spp_last_error(void);
+/* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
+uint64_t spp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 -- feature gather.  Replaces serial_index (fast_sampler/fast_sampler.cpp:238-279) and,
+ * on the GPU side of the reference, features_gpu[idx] (fast_trainer/transferers.py:649-653).
+ *   out[i, :] = table[idx[i], :]   for i < min(n_idx, n_out_rows)       (byte copy, any dtype)
+ * idx: int64 (idx_is_64 != 0) or int32.  If n_idx_dev != NULL the row count is read from
+ * device memory (*n_idx_dev, int64) and n_idx is only the upper bound used to size the grid.
+ * ---------------------------------------------------------------------------------------- */
+int spp_gather_rows(const void* table, int64_t row_bytes, const void* idx, int idx_is_64,
+                    int64_t n_idx, const int64_t* n_idx_dev, void* out, int64_t n_out_rows,
+                    void* stream);
+
+/* RangePartitionBook + feature placement used by the partitioned gather and the split.
+ * Mirrors RangePartitionBook{rank, world_size, partition_offsets}
+ * (fast_sampler/range_partition_book.hpp:31-57) and Cache (:60-91). */
+typedef struct spp_feature_map {
+  int32_t num_parts;                    /* world_size                                          */
+  int32_t rank;                         /* partition owned by this GPU                         */
+  int64_t offsets[SPP_MAX_PARTS + 1];   /* partition_offsets, offsets[0] = 0 ... [P] = N       */
+  const void* tables[SPP_MAX_PARTS];    /* tables[p]: rows of partition p (local HBM or a peer */
+                                        /* GPU's HBM mapped through CUDA IPC); may be NULL for */
+                                        /* partitions this GPU cannot reach                    */
+  const void* cache_table;              /* cached_features [C, F] or NULL                      */
+  const int32_t* cache_map;             /* dense int32[N]: cache row of a node id, -1 if none  */
+                                        /* (the reference keeps a dense map too,               */
+                                        /*  range_partition_book.cpp:152-158); NULL = no cache */
+} spp_feature_map;
+
+/* K4+K5 -- fused partition-book translate + cache lookup + local/cached gather + P2P miss
+ * fetch, written ONCE in MFG (n_id) order.  Replaces stages slicing1..4, the three
+ * all_to_alls and combine_features of fast_trainer/transferers.py:462-766:
+ *   p = nid2partid(n_id[i]);  row = p == rank ? tables[rank][n_id[i]-off[rank]]
+ *                                  : cached(n_id[i]) ? cache_table[cache_map[n_id[i]]]
+ *                                  : tables[p][n_id[i]-off[p]]           (peer HBM over NVLink)
+ * counters (optional, int64[3]): rows served local / cache / peer are ADDED to it. */
+int spp_gather_partitioned(const spp_feature_map* map_host, int64_t row_bytes, const void* n_id,
+                           int idx_is_64, int64_t n_idx, const int64_t* n_idx_dev, void* out,
+                           int64_t n_out_rows, int64_t* counters, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 -- RangePartitionBook kernels (fast_sampler/range_partition_book.cpp:89-107).
+ * ---------------------------------------------------------------------------------------- */
+/* out[i] = searchsorted(offsets, nids[i], right=True) - 1 */
+int spp_nid2partid(const int64_t* offsets_host, int num_parts, const int64_t* nids, int64_t n,
+                   int64_t* out, void* stream);
+/* out[i] = nids[i] - offsets[partition_idx] */
+int spp_nid2localnid(const int64_t* offsets_host, int num_parts, int partition_idx,
+                     const int64_t* nids, int64_t n, int64_t* out, void* stream);
+/* out[i] = offsets[rank] <= nids[i] < offsets[rank+1]   (bool bytes) */
+int spp_nid_is_local(const int64_t* offsets_host, int num_parts, int rank, const int64_t* nids,
+                     int64_t n, uint8_t* out, void* stream);
+
+/* Cache (fast_sampler/range_partition_book.cpp:116-195) */
+/* cache_map[v] = -1 for all v < num_nodes, then cache_map[cached_vertices[i]] = i (the largest
+ * i wins for a duplicated vertex, like the reference's sequential overwrite :154-158) */
+int spp_cache_build_map(const int64_t* cached_vertices, int64_t n_cached, int32_t* cache_map,
+                        int64_t num_nodes, void* stream);
+/* out[i] = cache_map[nids[i]] >= 0   (bool bytes) */
+int spp_nid_is_cached(const int32_t* cache_map, const int64_t* nids, int64_t n, uint8_t* out,
+                      void* stream);
+/* out[i] = cache_map[nids[i]]   (int64) */
+int spp_nid2cachenid(const int32_t* cache_map, const int64_t* nids, int64_t n, int64_t* out,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 -- distributed split of a mini-batch's node list (fast_sampler/fast_sampler.cpp:1017-1262).
+ * Stable split of n_id[0..n) into P+1 buckets -- bucket p < P: nodes fetched from partition p
+ * (own rank: every local node; others: remote and NOT cached), bucket P: remote cached nodes --
+ * each bucket in n_id order, concatenated in bucket order:
+ *   bucket_ids[pos]  = global id            (buckets 0..P-1, = partition_nids)
+ *                    = cache row index      (bucket P,       = cached_nids)
+ *   perm[i]          = pos of n_id[i]       (= perm_partition_to_mfg: cat(...)[perm] == n_id)
+ *   bucket_counts[b] = size of bucket b     (int64[P+1]); bucket_counts[P+1] = n
+ * use_cache == 0 reproduces the no-cache branch (:1031-1107).
+ * n_dev (optional): take n from device memory (upper bound n_max sizes the grid).
+ * scratch: int32[spp_split_scratch_words(n_max)] device words.
+ * ---------------------------------------------------------------------------------------- */
+int64_t spp_split_scratch_words(int64_t n_max);
+int spp_split_by_owner(const spp_feature_map* map_host, int use_cache, const void* n_id,
+                       int idx_is_64, int64_t n_max, const int64_t* n_dev, int64_t* bucket_ids,
+                       int64_t* perm, int64_t* bucket_counts, int32_t* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 -- multi-hop neighbour sampling with per-hop dedup and global->local relabelling.
+ * Replaces sample_adj (fast_sampler/sample_cpu.hpp:25-143) and multilayer_sample
+ * (fast_sampler/fast_sampler.cpp:191-236).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct spp_graph {
+  const int64_t* rowptr; /* int64[num_nodes + 1]                                              */
+  const void* col;       /* int32 or int64 [nnz]                                              */
+  int32_t col_is_64;
+  int32_t _pad;
+  int64_t num_nodes;
+} spp_graph;
+
+/* Per-stream scratch of the sampler (caller allocates; sizes from spp_sampler_sizes). */
+typedef struct spp_sampler_ws {
+  uint64_t* table;       /* hash table, table_slots entries of {key+1, ~local}                 */
+  int64_t table_slots;   /* power of two, >= 2 * max_nodes                                     */
+  int32_t* n_ids;        /* int32[max_nodes]   global ids in first-discovery order             */
+  int64_t max_nodes;
+  int64_t* tgt_start;    /* int64[max_targets] rowptr[n] of each frontier node                  */
+  int32_t* tgt_deg;      /* int32[max_targets]                                                  */
+  int64_t max_targets;   /* frontier bound of the last hop                                     */
+  uint64_t* tile_state;  /* uint64[tile_words] decoupled look-back state                        */
+  int64_t tile_words;
+  int64_t* meta;         /* int64[SPP_META_WORDS]                                               */
+} spp_sampler_ws;
+
+typedef struct spp_sampler_sizes_t {
+  int64_t max_nodes;        /* bound on |n_id|                                                 */
+  int64_t max_targets;      /* bound on the last hop's frontier                                */
+  int64_t table_slots;
+  int64_t tile_words;
+  int64_t hop_targets[SPP_MAX_HOPS]; /* bound T_h                                              */
+  int64_t hop_edges[SPP_MAX_HOPS];   /* bound E_h (-1: data dependent, full neighbourhood)     */
+} spp_sampler_sizes_t;
+
+/* Upper bounds for a batch of `batch_size` seeds and fanouts `sizes` (negative = all
+ * neighbours).  For full-neighbourhood hops the bounds need the graph: pass max_degree
+ * (any upper bound on the degree) and num_nodes; edges bound = targets * max_degree. */
+int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes_host, int n_hops, int64_t num_nodes,
+                      int64_t max_degree, spp_sampler_sizes_t* out_host);
+
+/* One mini-batch, all hops, no host synchronisation:
+ *   seeds        int64[batch_size]  (global ids; duplicates allowed, last position wins in the
+ *                                    id map exactly like sample_cpu.hpp:13-19)
+ *   sizes_host   fanout per hop, seed side first (fast_sampler.cpp:207); <0 = all neighbours
+ *   out_rowptr[h] int64[hop_targets[h] + 1], out_col[h] int64[hop_edges[h]]  (hop order, NOT
+ *                reversed: the host reverses like fast_sampler.cpp:224)
+ *   out_col_cap  capacity (elements) of each out_col[h]
+ *   n_id_out     int64[max_nodes] or NULL: widened n_id (fast_sampler.cpp:219-222)
+ *   rng_seed     key of the counter-based generator; a Session uses stop*17+5 like
+ *                fast_sampler.cpp:994
+ * Sampling rule per target (sample_cpu.hpp:67-113): deg <= k or k < 0: every neighbour in col
+ * order; otherwise Floyd's algorithm with t uniform on [0, j] (the reference's `% j` is a
+ * defect), neighbours emitted in Floyd order.  Local ids are assigned in
+ * sequential first-discovery order and each output row is sorted ascending.
+ * ws->meta receives the node / edge counts; SPP_META_OVERFLOW is set if a bound was hit. */
+int spp_sample_minibatch(const spp_graph* graph_host, const int64_t* seeds, int64_t batch_size,
+                         const int32_t* sizes_host, int n_hops, int replace, uint64_t rng_seed,
+                         const spp_sampler_ws* ws_host, int64_t* const* out_rowptr_host,
+                         int64_t* const* out_col_host, const int64_t* out_col_cap_host,
+                         int64_t* n_id_out, void* stream);
+
+/* Single-hop building blocks (used by sample_adj and by full-neighbourhood hops whose edge
+ * count must be known before out_col can be allocated):
+ *   begin : clear table, insert seeds                       -> meta[NODES(0)] = batch_size
+ *   count : degrees + exclusive scan -> out_rowptr, meta[EDGES(hop)]        (then the host may
+ *           read meta to size out_col)
+ *   fill  : sample + insert + compact + relabel/sort -> out_col, meta[NODES(hop+1)] */
+int spp_sample_begin(const spp_graph* graph_host, const int64_t* seeds, int64_t batch_size,
+                     const spp_sampler_ws* ws_host, void* stream);
+int spp_sample_hop_count(const spp_graph* graph_host, int hop, int32_t fanout, int replace,
+                         int64_t max_targets, const spp_sampler_ws* ws_host, int64_t* out_rowptr,
+                         void* stream);
+int spp_sample_hop_fill(const spp_graph* graph_host, int hop, int32_t fanout, int replace,
+                        uint64_t rng_seed, int64_t max_targets, int64_t max_edges,
+                        const spp_sampler_ws* ws_host, const int64_t* out_rowptr, int64_t* out_col,
+                        void* stream);
+/* n_id_out[i] = (int64) ws->n_ids[i], i < meta[NODES(hop)]  (or int32 copy if out_is_64 == 0) */
+int spp_sample_export_nids(const spp_sampler_ws* ws_host, int hop, void* n_id_out, int out_is_64,
+                           int64_t max_nodes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer mapping (CUDA IPC) for the P2P gather.  Host-synchronous.
+ *   export: handle_host receives 64 bytes, *offset_host the offset of `ptr` inside its
+ *           allocation; import (in another process) returns a device pointer valid there.
+ * ---------------------------------------------------------------------------------------- */
+int spp_ipc_export(const void* ptr, uint8_t* handle_host, int64_t* offset_host);
+int spp_ipc_import(const uint8_t* handle_host, int64_t offset, void** ptr_host);
+int spp_ipc_close(void* ptr, int64_t offset);
+int spp_enable_peer_access(int peer_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALIENT_B200_H_ */

@@ -1,0 +1,134 @@
+"""ctypes binding of ``libsalient_b200.so`` (the C ABI declared in ``include/salient_b200.h``).
+
+The library is the product: if it is missing this module raises -- there is no CPU or PyTorch
+fallback anywhere in the package.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make -C salient_plusplus_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import (POINTER, Structure, c_char_p, c_int, c_int32, c_int64, c_uint8, c_uint64,
+                    c_void_p)
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libsalient_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+SPP_MAX_PARTS = 16
+SPP_MAX_HOPS = 8
+SPP_MAX_FANOUT = 128
+SPP_META_WORDS = 32
+META_EDGES0 = 12
+META_OVERFLOW = 24
+
+EXPORTED = [
+    "spp_abi_version", "spp_last_error", "spp_launch_count",
+    "spp_gather_rows", "spp_gather_partitioned",
+    "spp_nid2partid", "spp_nid2localnid", "spp_nid_is_local",
+    "spp_cache_build_map", "spp_nid_is_cached", "spp_nid2cachenid",
+    "spp_split_scratch_words", "spp_split_by_owner",
+    "spp_sampler_sizes", "spp_sample_minibatch", "spp_sample_begin", "spp_sample_hop_count",
+    "spp_sample_hop_fill", "spp_sample_export_nids",
+    "spp_ipc_export", "spp_ipc_import", "spp_ipc_close", "spp_enable_peer_access",
+]
+
+
+class FeatureMap(Structure):
+    _fields_ = [("num_parts", c_int32), ("rank", c_int32),
+                ("offsets", c_int64 * (SPP_MAX_PARTS + 1)),
+                ("tables", c_void_p * SPP_MAX_PARTS),
+                ("cache_table", c_void_p), ("cache_map", c_void_p)]
+
+
+class Graph(Structure):
+    _fields_ = [("rowptr", c_void_p), ("col", c_void_p), ("col_is_64", c_int32), ("_pad", c_int32),
+                ("num_nodes", c_int64)]
+
+
+class SamplerWs(Structure):
+    _fields_ = [("table", c_void_p), ("table_slots", c_int64), ("n_ids", c_void_p),
+                ("max_nodes", c_int64), ("tgt_start", c_void_p), ("tgt_deg", c_void_p),
+                ("max_targets", c_int64), ("tile_state", c_void_p), ("tile_words", c_int64),
+                ("meta", c_void_p)]
+
+
+class SamplerSizes(Structure):
+    _fields_ = [("max_nodes", c_int64), ("max_targets", c_int64), ("table_slots", c_int64),
+                ("tile_words", c_int64), ("hop_targets", c_int64 * SPP_MAX_HOPS),
+                ("hop_edges", c_int64 * SPP_MAX_HOPS)]
+
+
+class SalientB200Error(RuntimeError):
+    """Raised for any non-zero return of the C ABI (mirrors the reference's TORCH_CHECK ->
+    RuntimeError behaviour, fast_sampler/fast_sampler.cpp:572-577)."""
+
+
+_lib = None
+
+
+def build_library(force: bool = False, quiet: bool = True) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-C", CSRC, "clean"], stdout=subprocess.DEVNULL)
+    out = subprocess.DEVNULL if quiet else None
+    subprocess.check_call(["make", "-C", CSRC, "-j", "4"], stdout=out)
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SalientB200Error(
+            f"{LIB_PATH} is missing: the CUDA library has not been built "
+            "(run `make -C salient_plusplus_b200/csrc`); there is no fallback path")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, i32, ci = c_void_p, c_int64, c_int32, c_int
+    L.spp_abi_version.restype = ci
+    L.spp_last_error.restype = c_char_p
+    L.spp_launch_count.restype = c_uint64
+    L.spp_gather_rows.argtypes = [vp, i64, vp, ci, i64, vp, vp, i64, vp]
+    L.spp_gather_partitioned.argtypes = [POINTER(FeatureMap), i64, vp, ci, i64, vp, vp, i64, vp, vp]
+    L.spp_nid2partid.argtypes = [POINTER(i64), ci, vp, i64, vp, vp]
+    L.spp_nid2localnid.argtypes = [POINTER(i64), ci, ci, vp, i64, vp, vp]
+    L.spp_nid_is_local.argtypes = [POINTER(i64), ci, ci, vp, i64, vp, vp]
+    L.spp_cache_build_map.argtypes = [vp, i64, vp, i64, vp]
+    L.spp_nid_is_cached.argtypes = [vp, vp, i64, vp, vp]
+    L.spp_nid2cachenid.argtypes = [vp, vp, i64, vp, vp]
+    L.spp_split_scratch_words.restype = i64
+    L.spp_split_scratch_words.argtypes = [i64]
+    L.spp_split_by_owner.argtypes = [POINTER(FeatureMap), ci, vp, ci, i64, vp, vp, vp, vp, vp, vp]
+    L.spp_sampler_sizes.argtypes = [i64, POINTER(i32), ci, i64, i64, POINTER(SamplerSizes)]
+    L.spp_sample_minibatch.argtypes = [POINTER(Graph), vp, i64, POINTER(i32), ci, ci, c_uint64,
+                                       POINTER(SamplerWs), POINTER(vp), POINTER(vp), POINTER(i64),
+                                       vp, vp]
+    L.spp_sample_begin.argtypes = [POINTER(Graph), vp, i64, POINTER(SamplerWs), vp]
+    L.spp_sample_hop_count.argtypes = [POINTER(Graph), ci, i32, ci, i64, POINTER(SamplerWs), vp, vp]
+    L.spp_sample_hop_fill.argtypes = [POINTER(Graph), ci, i32, ci, c_uint64, i64, i64,
+                                      POINTER(SamplerWs), vp, vp, vp]
+    L.spp_sample_export_nids.argtypes = [POINTER(SamplerWs), ci, vp, ci, i64, vp]
+    L.spp_ipc_export.argtypes = [vp, POINTER(c_uint8), POINTER(i64)]
+    L.spp_ipc_import.argtypes = [POINTER(c_uint8), i64, POINTER(vp)]
+    L.spp_ipc_close.argtypes = [vp, i64]
+    L.spp_enable_peer_access.argtypes = [ci]
+    for name in EXPORTED:
+        fn = getattr(L, name)  # raises AttributeError if a declared symbol is not exported
+        if fn.restype is ci and name not in ("spp_abi_version",):
+            pass
+    if L.spp_abi_version() != 1:
+        raise SalientB200Error("libsalient_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().spp_last_error().decode("utf-8", "replace")
+        raise SalientB200Error(f"{what or 'libsalient_b200'} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().spp_launch_count())

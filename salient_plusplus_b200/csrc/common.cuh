@@ -1,0 +1,136 @@
+// common.cuh -- shared host/device helpers of libsalient_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "salient_b200.h"
+
+namespace spp {
+
+// ---- host side -------------------------------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+int num_sms();
+
+#define SPP_CUDA(expr)                                        \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return spp::cuda_fail(_e, #expr);  \
+  } while (0)
+
+#define SPP_KERNEL_CHECK(name)                                   \
+  do {                                                           \
+    spp::count_launch();                                         \
+    cudaError_t _e = cudaGetLastError();                         \
+    if (_e != cudaSuccess) return spp::cuda_fail(_e, name);      \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device side -----------------------------------------------------------------------------
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+
+// Counter-based generator: specification shared with oracle/salient_oracle.c:spo_rand64.
+__host__ __device__ __forceinline__ uint64_t premix_seed(uint64_t seed) {
+  return mix64(seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull);
+}
+__device__ __forceinline__ uint64_t rand64(uint64_t premixed, uint32_t hop, uint64_t target_pos,
+                                           uint32_t pick) {
+  uint64_t ctr = ((uint64_t)hop << 56) ^ (target_pos << 8) ^ (uint64_t)pick;
+  return mix64(premixed ^ ctr);
+}
+// uniform integer in [0, range)
+__device__ __forceinline__ uint32_t bounded(uint64_t r, uint32_t range) {
+  return (uint32_t)__umul64hi(r, (uint64_t)range);
+}
+
+// 128-bit streaming loads/stores that do not allocate in L1 (gathered rows are touched once)
+__device__ __forceinline__ int4 ld_nc_na(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int2 ld_nc_na(const int2* p) {
+  int2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ld_nc_na(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ short ld_nc_na(const short* p) {
+  short r;
+  asm volatile("ld.global.nc.L1::no_allocate.s16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ char ld_nc_na(const char* p) { return *p; }
+
+__device__ __forceinline__ void st_na(int4* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_na(int2* p, const int2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.s32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_na(int* p, const int& v) {
+  asm volatile("st.global.L1::no_allocate.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_na(short* p, const short& v) { *p = v; }
+__device__ __forceinline__ void st_na(char* p, const char& v) { *p = v; }
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+  uint64_t r;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+  return v;
+}
+// inclusive scan across the 32 lanes of a warp
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(kFullMask, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+// Range partition book in kernel-parameter space (<= 17 offsets: a register-resident search)
+struct BookParams {
+  int64_t off[SPP_MAX_PARTS + 1];
+  int num_parts;
+  int rank;
+};
+// searchsorted(off, nid, right=True) - 1, clamped like the reference's use (ids inside [0, N))
+__device__ __forceinline__ int book_partid(const BookParams& b, int64_t nid) {
+  int p = 0;
+#pragma unroll
+  for (int q = 1; q < SPP_MAX_PARTS; ++q)
+    if (q < b.num_parts && nid >= b.off[q]) p = q;
+  return p;
+}
+
+}  // namespace spp

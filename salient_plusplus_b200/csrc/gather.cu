@@ -1,0 +1,214 @@
+// gather.cu -- K4 feature gather and K4+K5 fused partition-book / cache / peer-to-peer gather.
+//
+// HBM-bound byte movement: out[i,:] = table[idx[i],:].  One CTA owns a tile of kRows output rows:
+// it first resolves the tile's source row pointers into shared memory (index load, and for the
+// partitioned flavour the range-partition-book search + dense cache-map lookup + owner table
+// selection), then all 256 threads stream the tile as a flat run of 16-byte chunks: the output
+// side is perfectly coalesced (the tile is contiguous in `out`), the input side is coalesced
+// inside each row.  kUnroll independent 128-bit loads are in flight per thread before the first
+// store (L1::no_allocate on both sides: every byte is touched once).
+//
+// Algorithmic bytes per row: 2 * row_bytes + sizeof(index)   (DESIGN.md section 4).
+#include "common.cuh"
+
+namespace spp {
+
+constexpr int kGatherThreads = 256;
+constexpr int kRows = 64;   // rows per tile
+constexpr int kUnroll = 4;  // independent vector loads in flight per thread
+
+struct GatherParams {
+  const char* table;     // single-table flavour
+  const void* idx;       // int32 / int64 node or row ids
+  const int64_t* n_dev;  // optional device-resident row count
+  int64_t n_max;         // host-side bound (min(n_idx, n_out_rows))
+  char* out;
+  int64_t row_bytes;
+  uint32_t vpr;        // vectors per row
+  uint32_t vpr_magic;  // ceil(2^32 / vpr): lc / vpr == umulhi(lc, magic) while lc * vpr < 2^32;
+                       // 0 = use a real division (vpr == 1 or very wide rows)
+  // partitioned flavour
+  BookParams book;
+  const char* tables[SPP_MAX_PARTS];
+  const char* cache_table;
+  const int32_t* cache_map;
+  unsigned long long* counters;  // [3] local / cache / peer rows (optional)
+};
+
+template <typename V, bool kPartitioned, typename IdxT>
+__global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant__ GatherParams prm) {
+  __shared__ const char* s_src[kRows];
+  const int tid = threadIdx.x;
+  int64_t n = prm.n_max;
+  if (prm.n_dev != nullptr) {
+    int64_t nd = *prm.n_dev;
+    n = nd < n ? nd : n;
+  }
+  const int64_t num_tiles = (n + kRows - 1) / kRows;
+  const IdxT* __restrict__ idx = reinterpret_cast<const IdxT*>(prm.idx);
+  const uint32_t vpr = prm.vpr, magic = prm.vpr_magic;
+
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kRows;
+    const int rows = (int)((n - row0) < kRows ? (n - row0) : kRows);
+    __syncthreads();  // previous tile's s_src fully consumed
+    if (tid < kRows) {
+      int cls = -1;
+      if (tid < rows) {
+        const int64_t id = (int64_t)idx[row0 + tid];
+        if constexpr (!kPartitioned) {
+          s_src[tid] = prm.table + id * prm.row_bytes;
+        } else {
+          const int p = book_partid(prm.book, id);
+          const char* src;
+          if (p == prm.book.rank) {
+            src = prm.tables[p] + (id - prm.book.off[p]) * prm.row_bytes;
+            cls = 0;
+          } else {
+            int32_t crow = -1;
+            if (prm.cache_map != nullptr) crow = __ldg(prm.cache_map + id);
+            if (crow >= 0) {
+              src = prm.cache_table + (int64_t)crow * prm.row_bytes;
+              cls = 1;
+            } else {
+              src = prm.tables[p] + (id - prm.book.off[p]) * prm.row_bytes;  // peer HBM (NVLink)
+              cls = 2;
+            }
+          }
+          s_src[tid] = src;
+        }
+      }
+      if constexpr (kPartitioned) {
+        if (prm.counters != nullptr) {  // warps 0,1 are fully inside this branch
+          const uint32_t m0 = __ballot_sync(kFullMask, cls == 0);
+          const uint32_t m1 = __ballot_sync(kFullMask, cls == 1);
+          const uint32_t m2 = __ballot_sync(kFullMask, cls == 2);
+          if ((tid & 31) == 0) {
+            if (m0) atomicAdd(prm.counters + 0, (unsigned long long)__popc(m0));
+            if (m1) atomicAdd(prm.counters + 1, (unsigned long long)__popc(m1));
+            if (m2) atomicAdd(prm.counters + 2, (unsigned long long)__popc(m2));
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    const uint32_t chunks = (uint32_t)rows * vpr;
+    V* __restrict__ dst = reinterpret_cast<V*>(prm.out + row0 * prm.row_bytes);
+    for (uint32_t base = tid; base < chunks; base += kGatherThreads * kUnroll) {
+      V vals[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t lc = base + u * kGatherThreads;
+        if (lc < chunks) {
+          const uint32_t r = magic ? __umulhi(lc, magic) : lc / vpr;
+          const uint32_t v = lc - r * vpr;
+          vals[u] = ld_nc_na(reinterpret_cast<const V*>(s_src[r]) + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t lc = base + u * kGatherThreads;
+        if (lc < chunks) st_na(dst + lc, vals[u]);
+      }
+    }
+  }
+}
+
+template <bool kPartitioned>
+static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaStream_t st) {
+  if (prm.n_max <= 0) return 0;
+  prm.vpr = (uint32_t)(prm.row_bytes / vec_bytes);
+  if ((uint64_t)prm.vpr * kRows >= (1ull << 31))
+    return fail(SPP_EUNSUPPORTED, "gather: row of %lld bytes too wide", (long long)prm.row_bytes);
+  const bool magic_ok = prm.vpr > 1 && (uint64_t)kRows * prm.vpr * prm.vpr < (1ull << 32);
+  prm.vpr_magic = magic_ok ? (uint32_t)(((1ull << 32) + prm.vpr - 1) / prm.vpr) : 0u;
+  const int64_t tiles = ceil_div(prm.n_max, kRows);
+  const int64_t max_ctas = (int64_t)num_sms() * 8;
+  const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+#define SPP_GATHER_LAUNCH(V)                                                                    \
+  do {                                                                                          \
+    if (idx_is_64)                                                                              \
+      k_gather<V, kPartitioned, int64_t><<<grid, kGatherThreads, 0, st>>>(prm);                 \
+    else                                                                                        \
+      k_gather<V, kPartitioned, int32_t><<<grid, kGatherThreads, 0, st>>>(prm);                 \
+  } while (0)
+  switch (vec_bytes) {
+    case 16: SPP_GATHER_LAUNCH(int4); break;
+    case 8: SPP_GATHER_LAUNCH(int2); break;
+    case 4: SPP_GATHER_LAUNCH(int); break;
+    case 2: SPP_GATHER_LAUNCH(short); break;
+    default: SPP_GATHER_LAUNCH(char); break;
+  }
+#undef SPP_GATHER_LAUNCH
+  SPP_KERNEL_CHECK("k_gather");
+  return 0;
+}
+
+static int pick_vec_bytes(int64_t row_bytes, uintptr_t align_bits) {
+  for (int v = 16; v > 1; v >>= 1)
+    if (row_bytes % v == 0 && (align_bits % v) == 0) return v;
+  return 1;
+}
+
+}  // namespace spp
+
+extern "C" {
+
+int spp_gather_rows(const void* table, int64_t row_bytes, const void* idx, int idx_is_64, int64_t n_idx,
+                    const int64_t* n_idx_dev, void* out, int64_t n_out_rows, void* stream) {
+  using namespace spp;
+  if (row_bytes <= 0) return fail(SPP_EINVAL, "spp_gather_rows: row_bytes must be positive");
+  int64_t n = n_idx < n_out_rows ? n_idx : n_out_rows;
+  if (n <= 0) return 0;
+  if (!table || !idx || !out) return fail(SPP_EINVAL, "spp_gather_rows: null pointer");
+  GatherParams prm{};
+  prm.table = (const char*)table;
+  prm.idx = idx;
+  prm.n_dev = n_idx_dev;
+  prm.n_max = n;
+  prm.out = (char*)out;
+  prm.row_bytes = row_bytes;
+  int vb = pick_vec_bytes(row_bytes, (uintptr_t)table | (uintptr_t)out);
+  return launch_gather<false>(prm, vb, idx_is_64, (cudaStream_t)stream);
+}
+
+int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const void* n_id, int idx_is_64,
+                           int64_t n_idx, const int64_t* n_idx_dev, void* out, int64_t n_out_rows,
+                           int64_t* counters, void* stream) {
+  using namespace spp;
+  if (!m) return fail(SPP_EINVAL, "spp_gather_partitioned: null feature map");
+  if (m->num_parts < 1 || m->num_parts > SPP_MAX_PARTS || m->rank < 0 || m->rank >= m->num_parts)
+    return fail(SPP_EINVAL, "spp_gather_partitioned: bad num_parts/rank (%d/%d)", m->num_parts, m->rank);
+  if (row_bytes <= 0) return fail(SPP_EINVAL, "spp_gather_partitioned: row_bytes must be positive");
+  int64_t n = n_idx < n_out_rows ? n_idx : n_out_rows;
+  if (n <= 0) return 0;
+  if (!n_id || !out) return fail(SPP_EINVAL, "spp_gather_partitioned: null pointer");
+  if ((m->cache_map == nullptr) != (m->cache_table == nullptr))
+    return fail(SPP_EINVAL, "spp_gather_partitioned: cache_map and cache_table must be given together");
+  GatherParams prm{};
+  prm.idx = n_id;
+  prm.n_dev = n_idx_dev;
+  prm.n_max = n;
+  prm.out = (char*)out;
+  prm.row_bytes = row_bytes;
+  prm.book.num_parts = m->num_parts;
+  prm.book.rank = m->rank;
+  uintptr_t align = (uintptr_t)out;
+  for (int p = 0; p <= SPP_MAX_PARTS; ++p) prm.book.off[p] = p <= m->num_parts ? m->offsets[p] : m->offsets[m->num_parts];
+  for (int p = 0; p < m->num_parts; ++p) {
+    if (m->offsets[p + 1] < m->offsets[p]) return fail(SPP_EINVAL, "spp_gather_partitioned: offsets not sorted");
+    if (m->tables[p] == nullptr && m->offsets[p + 1] > m->offsets[p] && !(m->cache_map && p != m->rank))
+      return fail(SPP_EINVAL, "spp_gather_partitioned: partition %d has no table", p);
+    prm.tables[p] = (const char*)m->tables[p];
+    align |= (uintptr_t)m->tables[p];
+  }
+  prm.cache_table = (const char*)m->cache_table;
+  prm.cache_map = m->cache_map;
+  align |= (uintptr_t)m->cache_table;
+  prm.counters = (unsigned long long*)counters;
+  int vb = pick_vec_bytes(row_bytes, align);
+  return launch_gather<true>(prm, vb, idx_is_64, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,826 @@
+// sampler.cu -- K1: multi-hop uniform neighbour sampling over CSR with per-hop node dedup and
+// global->local relabelling.  Replaces sample_adj (fast_sampler/sample_cpu.hpp:25-143) and
+// multilayer_sample (fast_sampler/fast_sampler.cpp:191-236) of the reference.
+//
+// Per hop h (frontier = every node discovered so far, T of them; fan-out k):
+//   1. k_hop_count_scan   degree -> kept-edge count per target, single-pass decoupled look-back
+//                         scan -> out_rowptr (int64[T+1]); caches rowptr[n]/deg per target.
+//   2. k_hop_sample       a group of G lanes per target chooses the neighbours (all of them, k draws
+//                         with replacement, or Floyd's algorithm with a counter-based RNG), reads
+//                         col[], inserts the global id into the L2-resident hash table and
+//                         atomicMax-es ~(T + p) into the entry, p = global candidate position.
+//                         Established nodes hold ~local with local < T, so they always win;
+//                         a new node ends up holding the SMALLEST candidate position that saw it.
+//   3. k_hop_compact      order-preserving compaction (look-back scan) of the candidates that
+//                         own their entry (entry == ~(T + p)): the r-th such candidate defines
+//                         local id T + r.  This is exactly the sequential first-discovery order of
+//                         the reference (seeds, then row by row, neighbour by neighbour).
+//   4. k_relabel_sort_*   every row: candidate slot -> local id, ascending sort inside the row
+//                         (std::sort at sample_cpu.hpp:126), int64 output.
+//
+// Hash entry: 64 bits = { key + 1 , ~local } ; empty = 0, so the table is cleared by a memset.
+#include "common.cuh"
+
+namespace spp {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 1024 items per tile
+constexpr int kSampleThreads = 256;
+constexpr int kMetaWork = 25;       // meta word: number of rows queued for the large-row sorter
+constexpr int kWarpSortCap = 1024;  // rows up to this length are sorted by one warp in shared memory
+constexpr int kBlockSortSmemElems = 48 * 1024;  // int32 elements a CTA sorts in shared memory
+
+struct Table {
+  uint32_t* w;  // interleaved {key+1, ~local}
+  int shift;    // 32 - log2(slots)
+  uint32_t mask;
+};
+
+__device__ __forceinline__ uint32_t table_home(const Table& t, int32_t key) {
+  return ((uint32_t)key * 2654435761u) >> t.shift;
+}
+
+// insert-if-absent; returns the slot of `key`
+__device__ __forceinline__ uint32_t table_insert(const Table& t, int32_t key) {
+  const uint32_t want = (uint32_t)key + 1u;
+  uint32_t slot = table_home(t, key);
+  while (true) {
+    uint32_t k = __ldcg(t.w + 2 * (size_t)slot);
+    if (k == want) return slot;
+    if (k == 0u) {
+      uint32_t prev = atomicCAS(t.w + 2 * (size_t)slot, 0u, want);
+      if (prev == 0u || prev == want) return slot;
+    }
+    slot = (slot + 1) & t.mask;
+  }
+}
+
+__device__ __forceinline__ uint32_t table_find(const Table& t, int32_t key) {
+  const uint32_t want = (uint32_t)key + 1u;
+  uint32_t slot = table_home(t, key);
+  while (__ldcg(t.w + 2 * (size_t)slot) != want) slot = (slot + 1) & t.mask;
+  return slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// seeds: n_ids[i] = seeds[i]; map[seed] = LAST position of that seed (sample_cpu.hpp:13-19)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_seeds_init(const int64_t* __restrict__ seeds, int64_t bs,
+                                                     int32_t* __restrict__ n_ids, Table tab,
+                                                     int64_t* __restrict__ meta) {
+  const int tid = threadIdx.x;
+  for (int64_t i = tid; i < bs; i += blockDim.x) {
+    const int32_t key = (int32_t)seeds[i];
+    n_ids[i] = key;
+    const uint32_t slot = table_insert(tab, key);
+    atomicMax(tab.w + 2 * (size_t)slot + 1, (uint32_t)i + 1u);
+  }
+  __syncthreads();
+  for (int64_t i = tid; i < bs; i += blockDim.x) {
+    const uint32_t slot = table_find(tab, n_ids[i]);
+    uint32_t* enc = tab.w + 2 * (size_t)slot + 1;
+    if (__ldcg(enc) == (uint32_t)i + 1u) __stcg(enc, ~(uint32_t)i);
+  }
+  if (tid == 0) {
+    meta[SPP_META_NODES(0)] = bs;
+    meta[SPP_META_OVERFLOW] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoupled look-back scan machinery (tile_state[0] = dynamic tile counter, [1 + t] = tile t)
+// state word = status << 62 | value ; status 0 invalid, 1 aggregate, 2 inclusive prefix
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t kValMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* s_warp, uint64_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t t = __shfl_up_sync(kFullMask, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint64_t wbase = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    uint64_t x = s_warp[w];
+    if (w < warp) wbase += x;
+    tot += x;
+  }
+  total = tot;
+  __syncthreads();  // s_warp reusable
+  return wbase + inc - v;
+}
+
+// Called by every thread of the CTA; returns the exclusive prefix of `tile`.
+__device__ __forceinline__ uint64_t lookback(uint64_t* tile_state, int64_t tile, uint64_t aggregate,
+                                             uint64_t* s_bcast) {
+  uint64_t* st = tile_state + 1;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    uint64_t excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(st + 0, (2ull << 62) | (aggregate & kValMask));
+    } else {
+      if (lane == 0) st_volatile_u64(st + tile, (1ull << 62) | (aggregate & kValMask));
+      int64_t look = tile - 1;
+      while (true) {
+        const int64_t idx = look - lane;
+        uint64_t s = (2ull << 62);  // virtual zero prefix in front of tile 0
+        if (idx >= 0) {
+          do {
+            s = ld_volatile_u64(st + idx);
+          } while ((s >> 62) == 0);
+        }
+        const uint32_t pref = __ballot_sync(kFullMask, (s >> 62) == 2);
+        uint64_t v = s & kValMask;
+        if (pref) {
+          const int first = __ffs(pref) - 1;  // nearest tile holding an inclusive prefix
+          if (lane > first) v = 0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+        excl += v;
+        if (pref) break;
+        look -= 32;
+      }
+      if (lane == 0) st_volatile_u64(st + tile, (2ull << 62) | ((excl + aggregate) & kValMask));
+    }
+    if (lane == 0) *s_bcast = excl;
+  }
+  __syncthreads();
+  const uint64_t r = *s_bcast;
+  __syncthreads();
+  return r;
+}
+
+__device__ __forceinline__ int64_t next_tile(uint64_t* tile_state, int64_t* s_tile) {
+  if (threadIdx.x == 0) *s_tile = (int64_t)atomicAdd((unsigned long long*)tile_state, 1ull);
+  __syncthreads();
+  const int64_t t = *s_tile;
+  __syncthreads();
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. kept-edge count per target + exclusive scan
+// ------------------------------------------------------------------------------------------------
+struct HopParams {
+  const int64_t* rowptr;
+  const void* col;
+  int32_t* n_ids;
+  int64_t* tgt_start;
+  int32_t* tgt_deg;
+  int64_t* meta;
+  uint64_t* tile_state;
+  int64_t* out_rowptr;
+  int64_t* out_col;
+  Table tab;
+  int64_t max_targets;  // capacity of tgt_* / out_rowptr
+  int64_t max_edges;    // capacity of out_col
+  int64_t max_nodes;    // capacity of n_ids
+  uint64_t premixed;    // RNG key
+  int32_t hop;
+  int32_t fanout;
+  int32_t replace;
+};
+
+__global__ void __launch_bounds__(kScanThreads) k_hop_count_scan(const __grid_constant__ HopParams prm) {
+  __shared__ uint64_t s_warp[kScanThreads / 32];
+  __shared__ uint64_t s_bcast;
+  __shared__ int64_t s_tile;
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) {
+    T = prm.max_targets;
+    if (blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_OVERFLOW] = 1;
+  }
+  const int64_t num_tiles = (T + kScanTile - 1) / kScanTile;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    prm.out_rowptr[0] = 0;
+    prm.meta[kMetaWork] = 0;
+    if (T == 0) prm.meta[SPP_META_EDGES(prm.hop)] = 0;
+  }
+  const int k = prm.fanout;
+  while (true) {
+    const int64_t tile = next_tile(prm.tile_state, &s_tile);
+    if (tile >= num_tiles) break;
+    const int64_t i0 = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t c[kScanItems];
+    uint64_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+      const int64_t i = i0 + q;
+      c[q] = 0;
+      if (i < T) {
+        const int32_t n = prm.n_ids[i];
+        const int64_t s = __ldg(prm.rowptr + n), e = __ldg(prm.rowptr + n + 1);
+        const int32_t deg = (int32_t)(e - s);
+        prm.tgt_start[i] = s;
+        prm.tgt_deg[i] = deg;
+        uint32_t cnt;
+        if (k < 0) cnt = (uint32_t)deg;
+        else if (prm.replace) cnt = deg > 0 ? (uint32_t)k : 0u;
+        else cnt = (uint32_t)(deg < k ? deg : k);
+        c[q] = cnt;
+        sum += cnt;
+      }
+    }
+    uint64_t total;
+    const uint64_t texcl = block_excl_scan(sum, s_warp, total);
+    const uint64_t base = lookback(prm.tile_state, tile, total, &s_bcast);
+    uint64_t run = base + texcl;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+      const int64_t i = i0 + q;
+      run += c[q];
+      if (i < T) prm.out_rowptr[i + 1] = (int64_t)run;
+    }
+    if (tile == num_tiles - 1 && threadIdx.x == 0) prm.meta[SPP_META_EDGES(prm.hop)] = (int64_t)(base + total);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. neighbour choice + hash insert
+// ------------------------------------------------------------------------------------------------
+template <bool kCol64>
+__device__ __forceinline__ int32_t load_col(const void* col, int64_t e) {
+  if constexpr (kCol64) return (int32_t)__ldg(reinterpret_cast<const int64_t*>(col) + e);
+  else return __ldg(reinterpret_cast<const int32_t*>(col) + e);
+}
+
+__device__ __forceinline__ void emit_candidate(const HopParams& prm, int32_t node, uint32_t Tbase, int64_t p) {
+  const uint32_t slot = table_insert(prm.tab, node);
+  atomicMax(prm.tab.w + 2 * (size_t)slot + 1, ~(Tbase + (uint32_t)p));
+  prm.out_col[p] = (int64_t)slot;
+}
+
+// kMode 0: every neighbour (fanout < 0); 1: with replacement; 2: without replacement (Floyd)
+template <int kMode, int G, int PPL, bool kCol64>
+__global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_constant__ HopParams prm) {
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) T = prm.max_targets;
+  const int64_t E = prm.meta[SPP_META_EDGES(prm.hop)];
+  if (E > prm.max_edges || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_OVERFLOW] = 1;
+    return;
+  }
+  const uint32_t Tbase = (uint32_t)T;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);   // lane inside the group
+  const int gbase = lane & ~(G - 1);
+  constexpr int kGroupsPerWarp = 32 / G;
+  const int64_t warp_global = ((int64_t)blockIdx.x * kSampleThreads + threadIdx.x) >> 5;
+  const int64_t warps_total = ((int64_t)gridDim.x * kSampleThreads) >> 5;
+  const int k = prm.fanout;
+
+  for (int64_t i0 = warp_global * kGroupsPerWarp; i0 < T; i0 += warps_total * kGroupsPerWarp) {
+    const int64_t i = i0 + (lane / G);
+    const bool valid = i < T;
+    int64_t start = 0, p0 = 0;
+    int32_t deg = 0;
+    if (valid) {
+      start = prm.tgt_start[i];
+      deg = prm.tgt_deg[i];
+      p0 = prm.out_rowptr[i];
+    }
+    if constexpr (kMode == 0) {
+      for (int32_t j = gl; j < deg; j += G)
+        emit_candidate(prm, load_col<kCol64>(prm.col, start + j), Tbase, p0 + j);
+    } else if constexpr (kMode == 1) {
+      const int32_t c = deg > 0 ? k : 0;
+      for (int32_t j = gl; j < c; j += G) {
+        const uint32_t pick = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)j), (uint32_t)deg);
+        emit_candidate(prm, load_col<kCol64>(prm.col, start + pick), Tbase, p0 + j);
+      }
+    } else {
+      const bool need = valid && deg > k;
+      const int32_t basej = deg - k;
+      uint32_t myr[PPL], mypick[PPL];
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) {
+        const int j = gl + G * q;
+        myr[q] = 0;
+        mypick[q] = 0xffffffffu;
+        if (need && j < k)
+          myr[q] = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)j), (uint32_t)(basej + j) + 1u);
+      }
+      if (__any_sync(kFullMask, need)) {
+        // Floyd: step s draws t in [0, basej+s]; already chosen -> take basej+s instead.
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+#pragma unroll 1
+          for (int sl = 0; sl < G; ++sl) {
+            const int s = q * G + sl;
+            if (s >= k) break;
+            const uint32_t t = __shfl_sync(kFullMask, myr[q], gbase + sl);
+            bool hit = false;
+#pragma unroll
+            for (int q2 = 0; q2 < PPL; ++q2) hit |= (gl + G * q2 < s) && (mypick[q2] == t);
+            const uint32_t b = __ballot_sync(kFullMask, need && hit);
+            const uint32_t gm = (G == 32) ? b : ((b >> gbase) & ((1u << G) - 1u));
+            const uint32_t winner = gm ? (uint32_t)(basej + s) : t;
+            if (gl == sl) mypick[q] = winner;
+          }
+        }
+      }
+      const int32_t c = deg < k ? deg : k;
+      int32_t node[PPL];
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) {
+        const int j = gl + G * q;
+        if (valid && j < c) {
+          const uint32_t pick = need ? mypick[q] : (uint32_t)j;
+          node[q] = load_col<kCol64>(prm.col, start + pick);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) {
+        const int j = gl + G * q;
+        if (valid && j < c) emit_candidate(prm, node[q], Tbase, p0 + j);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. order-preserving compaction of first discoverers -> new local ids
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads) k_hop_compact(const __grid_constant__ HopParams prm) {
+  __shared__ uint64_t s_warp[kScanThreads / 32];
+  __shared__ uint64_t s_bcast;
+  __shared__ int64_t s_tile;
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) T = prm.max_targets;
+  int64_t E = prm.meta[SPP_META_EDGES(prm.hop)];
+  if (E > prm.max_edges || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) E = 0;  // overflow already flagged
+  const uint32_t Tbase = (uint32_t)T;
+  const int64_t num_tiles = (E + kScanTile - 1) / kScanTile;
+  if (E == 0 && blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_NODES(prm.hop + 1)] = T;
+  while (true) {
+    const int64_t tile = next_tile(prm.tile_state, &s_tile);
+    if (tile >= num_tiles) break;
+    const int64_t p0 = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t slot[kScanItems];
+    uint32_t flags = 0, cnt = 0;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+      const int64_t p = p0 + q;
+      slot[q] = 0;
+      if (p < E) {
+        slot[q] = (uint32_t)prm.out_col[p];
+        const uint32_t enc = __ldcg(prm.tab.w + 2 * (size_t)slot[q] + 1);
+        if (enc == ~(Tbase + (uint32_t)p)) {
+          flags |= 1u << q;
+          ++cnt;
+        }
+      }
+    }
+    uint64_t total;
+    const uint64_t texcl = block_excl_scan(cnt, s_warp, total);
+    const uint64_t base = lookback(prm.tile_state, tile, total, &s_bcast);
+    uint64_t r = base + texcl;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) {
+      if (flags & (1u << q)) {
+        const int64_t L = T + (int64_t)r;
+        if (L < prm.max_nodes) {
+          uint32_t* ent = prm.tab.w + 2 * (size_t)slot[q];
+          prm.n_ids[L] = (int32_t)(__ldcg(ent) - 1u);
+          __stcg(ent + 1, ~(uint32_t)L);
+        }
+        ++r;
+      }
+    }
+    if (tile == num_tiles - 1 && threadIdx.x == 0) {
+      int64_t S = T + (int64_t)(base + total);
+      if (S > prm.max_nodes) {
+        prm.meta[SPP_META_OVERFLOW] = 1;
+        S = prm.max_nodes;
+      }
+      prm.meta[SPP_META_NODES(prm.hop + 1)] = S;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4. relabel + per-row ascending sort
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ int32_t group_bitonic_sort(int32_t v, int gl) {
+#pragma unroll
+  for (int k = 2; k <= G; k <<= 1) {
+#pragma unroll
+    for (int d = k >> 1; d > 0; d >>= 1) {
+      const int32_t o = __shfl_xor_sync(kFullMask, v, d);
+      const bool lower = (gl & d) == 0;
+      const bool asc = (gl & k) == 0 || k == G;
+      const bool take_min = lower == asc;
+      v = take_min ? (v < o ? v : o) : (v > o ? v : o);
+    }
+  }
+  return v;
+}
+
+// every row has at most G entries (sampled hops with fanout <= 32)
+template <int G>
+__global__ void __launch_bounds__(kSampleThreads) k_relabel_sort_small(const __grid_constant__ HopParams prm) {
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) T = prm.max_targets;
+  if (prm.meta[SPP_META_OVERFLOW]) return;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  constexpr int kGroupsPerWarp = 32 / G;
+  const int64_t warp_global = ((int64_t)blockIdx.x * kSampleThreads + threadIdx.x) >> 5;
+  const int64_t warps_total = ((int64_t)gridDim.x * kSampleThreads) >> 5;
+  for (int64_t i0 = warp_global * kGroupsPerWarp; i0 < T; i0 += warps_total * kGroupsPerWarp) {
+    const int64_t i = i0 + (lane / G);
+    int64_t p0 = 0;
+    int n = 0;
+    if (i < T) {
+      p0 = prm.out_rowptr[i];
+      n = (int)(prm.out_rowptr[i + 1] - p0);
+    }
+    int32_t v = 0x7fffffff;
+    if (gl < n) {
+      const uint32_t slot = (uint32_t)prm.out_col[p0 + gl];
+      v = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
+    }
+    v = group_bitonic_sort<G>(v, gl);
+    if (gl < n) prm.out_col[p0 + gl] = (int64_t)v;
+  }
+}
+
+// compare-exchange network that sorts n (arbitrary) elements ascending: bitonic sort with the
+// "flip" first stage so every comparator is ascending and the virtual +inf padding never moves
+template <typename T, typename SyncF>
+__device__ __forceinline__ void network_sort(T* a, int64_t n, int tid, int nthreads, SyncF sync) {
+  for (int64_t k = 2; (k >> 1) < n; k <<= 1) {
+    for (int64_t i = tid; i < n; i += nthreads) {
+      const int64_t j = i ^ (k - 1);
+      if (j > i && j < n) {
+        const T x = a[i], y = a[j];
+        if (y < x) { a[i] = y; a[j] = x; }
+      }
+    }
+    sync();
+    for (int64_t d = k >> 2; d > 0; d >>= 1) {
+      for (int64_t i = tid; i < n; i += nthreads) {
+        const int64_t j = i ^ d;
+        if (j > i && j < n) {
+          const T x = a[i], y = a[j];
+          if (y < x) { a[i] = y; a[j] = x; }
+        }
+      }
+      sync();
+    }
+  }
+}
+
+// general rows: <= 32 in registers, <= kWarpSortCap in the warp's shared-memory slice, longer rows
+// are relabelled in place and queued (row index into tgt_deg, count in meta[kMetaWork])
+constexpr int kGeneralWarps = 4;
+__global__ void __launch_bounds__(kGeneralWarps * 32) k_relabel_sort_general(const __grid_constant__ HopParams prm) {
+  __shared__ int32_t s_buf[kGeneralWarps][kWarpSortCap];
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) T = prm.max_targets;
+  if (prm.meta[SPP_META_OVERFLOW]) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_global = (int64_t)blockIdx.x * kGeneralWarps + warp;
+  const int64_t warps_total = (int64_t)gridDim.x * kGeneralWarps;
+  int32_t* buf = s_buf[warp];
+  for (int64_t i = warp_global; i < T; i += warps_total) {
+    const int64_t p0 = prm.out_rowptr[i];
+    const int64_t n = prm.out_rowptr[i + 1] - p0;
+    if (n <= 32) {
+      int32_t v = 0x7fffffff;
+      if (lane < n) {
+        const uint32_t slot = (uint32_t)prm.out_col[p0 + lane];
+        v = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
+      }
+      v = group_bitonic_sort<32>(v, lane);
+      if (lane < n) prm.out_col[p0 + lane] = (int64_t)v;
+    } else if (n <= kWarpSortCap) {
+      for (int64_t j = lane; j < n; j += 32) {
+        const uint32_t slot = (uint32_t)prm.out_col[p0 + j];
+        buf[j] = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
+      }
+      __syncwarp();
+      network_sort(buf, n, lane, 32, [] { __syncwarp(); });
+      for (int64_t j = lane; j < n; j += 32) prm.out_col[p0 + j] = (int64_t)buf[j];
+      __syncwarp();
+    } else {
+      for (int64_t j = lane; j < n; j += 32) {
+        const uint32_t slot = (uint32_t)prm.out_col[p0 + j];
+        prm.out_col[p0 + j] = (int64_t)(int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
+      }
+      if (lane == 0) {
+        const unsigned long long w = atomicAdd((unsigned long long*)(prm.meta + kMetaWork), 1ull);
+        prm.tgt_deg[w] = (int32_t)i;  // tgt_deg is dead after k_hop_sample: reuse as the work list
+      }
+    }
+  }
+}
+
+// one CTA per queued long row
+__global__ void __launch_bounds__(256) k_sort_large_rows(const __grid_constant__ HopParams prm) {
+  extern __shared__ int32_t s_big[];
+  const int64_t work = prm.meta[kMetaWork];
+  for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
+    const int64_t i = prm.tgt_deg[w];
+    const int64_t p0 = prm.out_rowptr[i];
+    const int64_t n = prm.out_rowptr[i + 1] - p0;
+    int64_t* row = prm.out_col + p0;
+    if (n <= kBlockSortSmemElems) {
+      for (int64_t j = threadIdx.x; j < n; j += blockDim.x) s_big[j] = (int32_t)row[j];
+      __syncthreads();
+      network_sort(s_big, n, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+      for (int64_t j = threadIdx.x; j < n; j += blockDim.x) row[j] = (int64_t)s_big[j];
+      __syncthreads();
+    } else {
+      __syncthreads();
+      network_sort(row, n, threadIdx.x, blockDim.x, [] { __syncthreads(); });
+    }
+  }
+}
+
+template <typename OutT>
+__global__ void k_export_nids(const int32_t* __restrict__ n_ids, const int64_t* __restrict__ meta, int word,
+                              int64_t max_nodes, OutT* __restrict__ out) {
+  int64_t n = meta[word];
+  if (n > max_nodes) n = max_nodes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (OutT)n_ids[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int check_ws(const spp_sampler_ws* ws) {
+  if (!ws) return fail(SPP_EINVAL, "sampler: null workspace");
+  if (!ws->table || !ws->n_ids || !ws->tgt_start || !ws->tgt_deg || !ws->tile_state || !ws->meta)
+    return fail(SPP_EINVAL, "sampler: workspace has null members");
+  if (ws->table_slots < 2 || (ws->table_slots & (ws->table_slots - 1)) || ws->table_slots > (1ll << 31))
+    return fail(SPP_EINVAL, "sampler: table_slots must be a power of two in [2, 2^31]");
+  if (ws->table_slots < 2 * ws->max_nodes)
+    return fail(SPP_ECAPACITY, "sampler: table_slots (%lld) < 2 * max_nodes (%lld)", (long long)ws->table_slots,
+                (long long)ws->max_nodes);
+  return 0;
+}
+
+static Table make_table(const spp_sampler_ws* ws) {
+  Table t;
+  t.w = reinterpret_cast<uint32_t*>(ws->table);
+  int lg = 0;
+  while ((1ll << lg) < ws->table_slots) ++lg;
+  t.shift = 32 - lg;
+  t.mask = (uint32_t)(ws->table_slots - 1);
+  return t;
+}
+
+static HopParams make_params(const spp_graph* g, const spp_sampler_ws* ws, int hop, int32_t fanout, int replace,
+                             uint64_t rng_seed, int64_t max_targets, int64_t max_edges, int64_t* out_rowptr,
+                             int64_t* out_col) {
+  HopParams p{};
+  p.rowptr = g->rowptr;
+  p.col = g->col;
+  p.n_ids = ws->n_ids;
+  p.tgt_start = ws->tgt_start;
+  p.tgt_deg = ws->tgt_deg;
+  p.meta = ws->meta;
+  p.tile_state = ws->tile_state;
+  p.out_rowptr = out_rowptr;
+  p.out_col = out_col;
+  p.tab = make_table(ws);
+  p.max_targets = max_targets < ws->max_targets ? max_targets : ws->max_targets;
+  p.max_edges = max_edges;
+  p.max_nodes = ws->max_nodes;
+  p.premixed = premix_seed(rng_seed);
+  p.hop = hop;
+  p.fanout = fanout;
+  p.replace = replace;
+  return p;
+}
+
+static int scan_grid(int64_t bound_items) {
+  int64_t tiles = ceil_div(bound_items > 0 ? bound_items : 1, kScanTile);
+  int64_t cap = (int64_t)num_sms() * 4;
+  return (int)(tiles < cap ? tiles : cap);
+}
+
+static int reset_tiles(const spp_sampler_ws* ws, int64_t bound_items, cudaStream_t st) {
+  int64_t words = 1 + ceil_div(bound_items > 0 ? bound_items : 1, kScanTile);
+  if (words > ws->tile_words)
+    return fail(SPP_ECAPACITY, "sampler: tile_state too small (%lld words needed, %lld given)", (long long)words,
+                (long long)ws->tile_words);
+  SPP_CUDA(cudaMemsetAsync(ws->tile_state, 0, (size_t)words * sizeof(uint64_t), st));
+  return 0;
+}
+
+static int launch_begin(const spp_graph* g, const int64_t* seeds, int64_t bs, const spp_sampler_ws* ws,
+                        cudaStream_t st) {
+  if (int r = check_ws(ws)) return r;
+  if (!g || !g->rowptr || (!g->col && g->num_nodes > 0)) return fail(SPP_EINVAL, "sampler: null graph");
+  if (bs < 0 || bs > ws->max_nodes) return fail(SPP_ECAPACITY, "sampler: batch_size %lld exceeds max_nodes %lld",
+                                                 (long long)bs, (long long)ws->max_nodes);
+  if (bs > 0 && !seeds) return fail(SPP_EINVAL, "sampler: null seeds");
+  SPP_CUDA(cudaMemsetAsync(ws->table, 0, (size_t)ws->table_slots * sizeof(uint64_t), st));
+  k_seeds_init<<<1, 1024, 0, st>>>(seeds, bs, ws->n_ids, make_table(ws), ws->meta);
+  SPP_KERNEL_CHECK("k_seeds_init");
+  return 0;
+}
+
+static int launch_count(const spp_graph* g, int hop, int32_t fanout, int replace, int64_t max_targets,
+                        const spp_sampler_ws* ws, int64_t* out_rowptr, cudaStream_t st) {
+  if (hop < 0 || hop >= SPP_MAX_HOPS) return fail(SPP_EINVAL, "sampler: hop %d out of range", hop);
+  if (!out_rowptr) return fail(SPP_EINVAL, "sampler: null out_rowptr");
+  if (int r = reset_tiles(ws, max_targets, st)) return r;
+  HopParams p = make_params(g, ws, hop, fanout, replace, 0, max_targets, 0, out_rowptr, nullptr);
+  k_hop_count_scan<<<scan_grid(p.max_targets), kScanThreads, 0, st>>>(p);
+  SPP_KERNEL_CHECK("k_hop_count_scan");
+  return 0;
+}
+
+template <int kMode, int G, int PPL>
+static void launch_sample_kernel(const HopParams& p, bool col64, int grid, cudaStream_t st) {
+  if (col64) k_hop_sample<kMode, G, PPL, true><<<grid, kSampleThreads, 0, st>>>(p);
+  else k_hop_sample<kMode, G, PPL, false><<<grid, kSampleThreads, 0, st>>>(p);
+}
+
+static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace, uint64_t rng_seed,
+                       int64_t max_targets, int64_t max_edges, const spp_sampler_ws* ws, const int64_t* out_rowptr,
+                       int64_t* out_col, cudaStream_t st) {
+  if (hop < 0 || hop >= SPP_MAX_HOPS) return fail(SPP_EINVAL, "sampler: hop %d out of range", hop);
+  if (!out_rowptr || (!out_col && max_edges > 0)) return fail(SPP_EINVAL, "sampler: null output");
+  if (fanout >= 0 && !replace && fanout > SPP_MAX_FANOUT)
+    return fail(SPP_EUNSUPPORTED, "sampler: fanout %d > SPP_MAX_FANOUT (%d)", fanout, SPP_MAX_FANOUT);
+  HopParams p = make_params(g, ws, hop, fanout, replace, rng_seed, max_targets, max_edges,
+                            const_cast<int64_t*>(out_rowptr), out_col);
+  const bool c64 = g->col_is_64 != 0;
+  const int sms = num_sms();
+  // groups needed ~ targets; persistent grid, 8 CTAs / SM at most
+  auto grid_for = [&](int G) {
+    int64_t warps = ceil_div(p.max_targets > 0 ? p.max_targets : 1, 32 / G);
+    int64_t ctas = ceil_div(warps, kSampleThreads / 32);
+    int64_t cap = (int64_t)sms * 8;
+    return (int)(ctas < cap ? ctas : cap);
+  };
+  if (fanout < 0) {
+    launch_sample_kernel<0, 32, 1>(p, c64, grid_for(32), st);
+  } else if (replace) {
+    if (fanout <= 8) launch_sample_kernel<1, 8, 1>(p, c64, grid_for(8), st);
+    else if (fanout <= 16) launch_sample_kernel<1, 16, 1>(p, c64, grid_for(16), st);
+    else launch_sample_kernel<1, 32, 1>(p, c64, grid_for(32), st);
+  } else {
+    if (fanout <= 4) launch_sample_kernel<2, 4, 1>(p, c64, grid_for(4), st);
+    else if (fanout <= 8) launch_sample_kernel<2, 8, 1>(p, c64, grid_for(8), st);
+    else if (fanout <= 16) launch_sample_kernel<2, 16, 1>(p, c64, grid_for(16), st);
+    else if (fanout <= 32) launch_sample_kernel<2, 32, 1>(p, c64, grid_for(32), st);
+    else if (fanout <= 64) launch_sample_kernel<2, 32, 2>(p, c64, grid_for(32), st);
+    else launch_sample_kernel<2, 32, 4>(p, c64, grid_for(32), st);
+  }
+  SPP_KERNEL_CHECK("k_hop_sample");
+
+  if (int r = reset_tiles(ws, max_edges, st)) return r;
+  k_hop_compact<<<scan_grid(max_edges), kScanThreads, 0, st>>>(p);
+  SPP_KERNEL_CHECK("k_hop_compact");
+
+  const bool small_rows = fanout >= 0 && fanout <= 32;
+  if (small_rows) {
+    const int G = fanout <= 4 ? 4 : fanout <= 8 ? 8 : fanout <= 16 ? 16 : 32;
+    const int grid = grid_for(G);
+    switch (G) {
+      case 4: k_relabel_sort_small<4><<<grid, kSampleThreads, 0, st>>>(p); break;
+      case 8: k_relabel_sort_small<8><<<grid, kSampleThreads, 0, st>>>(p); break;
+      case 16: k_relabel_sort_small<16><<<grid, kSampleThreads, 0, st>>>(p); break;
+      default: k_relabel_sort_small<32><<<grid, kSampleThreads, 0, st>>>(p); break;
+    }
+    SPP_KERNEL_CHECK("k_relabel_sort_small");
+  } else {
+    int64_t ctas = ceil_div(p.max_targets > 0 ? p.max_targets : 1, kGeneralWarps);
+    int64_t cap = (int64_t)sms * 8;
+    k_relabel_sort_general<<<(int)(ctas < cap ? ctas : cap), kGeneralWarps * 32, 0, st>>>(p);
+    SPP_KERNEL_CHECK("k_relabel_sort_general");
+    if (fanout < 0 || fanout > kWarpSortCap) {
+      static bool attr_set = false;
+      const size_t smem = (size_t)kBlockSortSmemElems * sizeof(int32_t);
+      if (!attr_set) {
+        SPP_CUDA(cudaFuncSetAttribute(k_sort_large_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      k_sort_large_rows<<<sms, 256, smem, st>>>(p);
+      SPP_KERNEL_CHECK("k_sort_large_rows");
+    }
+  }
+  return 0;
+}
+
+static int launch_export(const spp_sampler_ws* ws, int word, void* out, int out_is_64, int64_t max_nodes,
+                         cudaStream_t st) {
+  if (!out || max_nodes <= 0) return 0;
+  int64_t cap = max_nodes < ws->max_nodes ? max_nodes : ws->max_nodes;
+  int64_t ctas = ceil_div(cap, 256);
+  int64_t lim = (int64_t)num_sms() * 8;
+  int grid = (int)(ctas < lim ? ctas : lim);
+  if (out_is_64) k_export_nids<int64_t><<<grid, 256, 0, st>>>(ws->n_ids, ws->meta, word, cap, (int64_t*)out);
+  else k_export_nids<int32_t><<<grid, 256, 0, st>>>(ws->n_ids, ws->meta, word, cap, (int32_t*)out);
+  SPP_KERNEL_CHECK("k_export_nids");
+  return 0;
+}
+
+}  // namespace spp
+
+extern "C" {
+
+int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes, int n_hops, int64_t num_nodes, int64_t max_degree,
+                      spp_sampler_sizes_t* out) {
+  using namespace spp;
+  if (!out || (n_hops > 0 && !sizes)) return fail(SPP_EINVAL, "spp_sampler_sizes: null argument");
+  if (n_hops < 0 || n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_sampler_sizes: n_hops %d out of range", n_hops);
+  if (batch_size < 0) return fail(SPP_EINVAL, "spp_sampler_sizes: negative batch size");
+  int64_t T = batch_size, maxE = 0, maxT = batch_size;
+  const int64_t node_cap = num_nodes > 0 ? batch_size + num_nodes : INT64_MAX;
+  for (int h = 0; h < n_hops; ++h) {
+    out->hop_targets[h] = T;
+    maxT = T;
+    int64_t k = sizes[h];
+    int64_t E;
+    if (k >= 0) {
+      int64_t per = (max_degree > 0 && max_degree < k) ? max_degree : k;
+      E = T * per;
+    } else if (max_degree >= 0) {
+      E = T * max_degree;
+    } else {
+      return fail(SPP_EINVAL, "spp_sampler_sizes: full-neighbourhood hop needs max_degree");
+    }
+    out->hop_edges[h] = E;
+    if (E > maxE) maxE = E;
+    int64_t next = T + E;
+    T = next < node_cap ? next : node_cap;
+  }
+  for (int h = n_hops; h < SPP_MAX_HOPS; ++h) out->hop_targets[h] = out->hop_edges[h] = 0;
+  out->max_nodes = T > 0 ? T : 1;
+  out->max_targets = maxT > 0 ? maxT : 1;
+  int64_t slots = 1024;
+  while (slots < 2 * out->max_nodes) slots <<= 1;
+  if (slots > (1ll << 31)) return fail(SPP_EUNSUPPORTED, "spp_sampler_sizes: node bound %lld too large", (long long)T);
+  out->table_slots = slots;
+  int64_t items = maxE > maxT ? maxE : maxT;
+  out->tile_words = 2 + ceil_div(items > 0 ? items : 1, kScanTile) + 30;
+  return 0;
+}
+
+int spp_sample_begin(const spp_graph* g, const int64_t* seeds, int64_t batch_size, const spp_sampler_ws* ws,
+                     void* stream) {
+  return spp::launch_begin(g, seeds, batch_size, ws, (cudaStream_t)stream);
+}
+
+int spp_sample_hop_count(const spp_graph* g, int hop, int32_t fanout, int replace, int64_t max_targets,
+                         const spp_sampler_ws* ws, int64_t* out_rowptr, void* stream) {
+  if (int r = spp::check_ws(ws)) return r;
+  return spp::launch_count(g, hop, fanout, replace, max_targets, ws, out_rowptr, (cudaStream_t)stream);
+}
+
+int spp_sample_hop_fill(const spp_graph* g, int hop, int32_t fanout, int replace, uint64_t rng_seed,
+                        int64_t max_targets, int64_t max_edges, const spp_sampler_ws* ws, const int64_t* out_rowptr,
+                        int64_t* out_col, void* stream) {
+  if (int r = spp::check_ws(ws)) return r;
+  return spp::launch_fill(g, hop, fanout, replace, rng_seed, max_targets, max_edges, ws, out_rowptr, out_col,
+                          (cudaStream_t)stream);
+}
+
+int spp_sample_export_nids(const spp_sampler_ws* ws, int hop, void* n_id_out, int out_is_64, int64_t max_nodes,
+                           void* stream) {
+  if (int r = spp::check_ws(ws)) return r;
+  if (hop < 0 || hop > SPP_MAX_HOPS) return spp::fail(SPP_EINVAL, "spp_sample_export_nids: hop out of range");
+  return spp::launch_export(ws, SPP_META_NODES(hop), n_id_out, out_is_64, max_nodes, (cudaStream_t)stream);
+}
+
+int spp_sample_minibatch(const spp_graph* g, const int64_t* seeds, int64_t batch_size, const int32_t* sizes,
+                         int n_hops, int replace, uint64_t rng_seed, const spp_sampler_ws* ws,
+                         int64_t* const* out_rowptr, int64_t* const* out_col, const int64_t* out_col_cap,
+                         int64_t* n_id_out, void* stream) {
+  using namespace spp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_hops < 0 || n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_sample_minibatch: n_hops out of range");
+  if (n_hops > 0 && (!sizes || !out_rowptr || !out_col || !out_col_cap))
+    return fail(SPP_EINVAL, "spp_sample_minibatch: null argument");
+  if (int r = launch_begin(g, seeds, batch_size, ws, st)) return r;
+  // host-side frontier bounds (the device clamps to them and raises SPP_META_OVERFLOW)
+  int64_t T = batch_size;
+  for (int h = 0; h < n_hops; ++h) {
+    int64_t Tb = T < ws->max_targets ? T : ws->max_targets;
+    if (int r = launch_count(g, h, sizes[h], replace, Tb, ws, out_rowptr[h], st)) return r;
+    if (int r = launch_fill(g, h, sizes[h], replace, rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st))
+      return r;
+    int64_t next = T + out_col_cap[h];
+    T = next < ws->max_nodes ? next : ws->max_nodes;
+  }
+  if (n_id_out) return launch_export(ws, SPP_META_NODES(n_hops), n_id_out, 1, ws->max_nodes, st);
+  return 0;
+}
+
+}  // extern "C"

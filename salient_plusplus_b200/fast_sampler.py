@@ -1,0 +1,871 @@
+"""GPU-native stand-in for the reference's pybind11 module ``fast_sampler``
+(fast_sampler/fast_sampler.cpp:1280-1396): same names, argument meaning and error behaviour --
+``Config``, ``Session``, ``ProtoDistributedBatch``, ``RangePartitionBook``, ``Cache``,
+``sample_adj``, ``multilayer_sample``, ``full_sample``, ``serial_index``, ``to_row_major`` -- with
+every operation executed by the sm_100a kernels of ``libsalient_b200.so`` through its C ABI
+(``include/salient_b200.h``).  PyTorch is used for device memory, streams and events only.
+
+Differences a caller can observe (all documented in INTEGRATION.md):
+  * returned tensors live in HBM (the reference returns pinned host tensors that the caller then
+    copies to the GPU; ``PreparedBatch.to(device)`` on our tensors is a no-op);
+  * stochastic sampling uses a counter-based generator and the *correct* Floyd step, so sampled
+    neighbourhoods differ from the reference's mt19937 stream (which is provably non-uniform,
+    fast_sampler/sample_cpu.hpp:99); deterministic paths are bit-exact;
+  * ``num_threads`` is accepted and ignored: parallelism comes from the GPU, batches are kept in
+    flight on ``min(max_items_in_queue, SPP_SESSION_DEPTH)`` CUDA streams.
+There is no CPU fallback: without a CUDA device or without the built library every entry point
+raises.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes
+import datetime
+import os
+import time
+from collections import OrderedDict, deque
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (META_EDGES0, META_OVERFLOW, SPP_MAX_HOPS, SPP_MAX_PARTS, SPP_META_WORDS,
+                   FeatureMap, Graph, SalientB200Error, SamplerSizes, SamplerWs, check)
+
+__all__ = ["Config", "Session", "ProtoDistributedBatch", "RangePartitionBook", "Cache", "sample_adj",
+           "multilayer_sample", "full_sample", "serial_index", "to_row_major"]
+
+c_vp = ctypes.c_void_p
+
+
+# ------------------------------------------------------------------------------------------------
+# device plumbing
+# ------------------------------------------------------------------------------------------------
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise SalientB200Error("no CUDA device visible: salient_plusplus_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> int:
+    return (stream or torch.cuda.current_stream()).cuda_stream
+
+
+_RESIDENT: "OrderedDict[tuple, tuple]" = OrderedDict()
+_RESIDENT_MAX = 32
+
+
+def _resident(t: torch.Tensor, dtype: Optional[torch.dtype] = None, tag: str = "") -> torch.Tensor:
+    """Device-resident, contiguous copy of ``t`` (uploaded once and cached while the source
+    tensor is alive -- graph structure and feature tables are set-up state, not per-batch input)."""
+    dev = _device()
+    if t.is_cuda and t.is_contiguous() and (dtype is None or t.dtype == dtype):
+        return t
+    key = (t.data_ptr(), tuple(t.shape), t.dtype, t._version, dtype, tag, dev.index, t.device.type)
+    hit = _RESIDENT.get(key)
+    if hit is not None:
+        _RESIDENT.move_to_end(key)
+        return hit[1]
+    d = t.to(device=dev, non_blocking=False)
+    if dtype is not None and d.dtype != dtype:
+        d = d.to(dtype)
+    d = d.contiguous()
+    _RESIDENT[key] = (t, d)  # keep the source alive so its data_ptr cannot be recycled
+    while len(_RESIDENT) > _RESIDENT_MAX:
+        _RESIDENT.popitem(last=False)
+    return d
+
+
+def clear_resident_cache() -> None:
+    _RESIDENT.clear()
+
+
+class _DeviceGraph:
+    """CSR in HBM: int64 rowptr, int32 col (ids < 2^31, the reference narrows too,
+    fast_sampler/fast_sampler.cpp:196-199)."""
+
+    _cache: "OrderedDict[tuple, _DeviceGraph]" = OrderedDict()
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor):
+        if rowptr.dim() != 1 or col.dim() != 1 or rowptr.numel() < 1:
+            raise RuntimeError("rowptr/col must be 1-D CSR arrays")
+        self.num_nodes = rowptr.numel() - 1
+        if self.num_nodes >= 2 ** 31:
+            raise RuntimeError("graphs with >= 2^31 nodes are not supported")
+        self.rowptr = _resident(rowptr, torch.int64, "rowptr")
+        if col.dtype == torch.int32:
+            self.col = _resident(col, torch.int32, "col")
+        else:
+            self.col = _resident(col, torch.int32, "col32")
+        self.nnz = col.numel()
+        if self.num_nodes > 0:
+            deg = self.rowptr[1:] - self.rowptr[:-1]
+            self.max_degree = int(deg.max().item())
+        else:
+            self.max_degree = 0
+        self.c = Graph(self.rowptr.data_ptr(), self.col.data_ptr(), 0, 0, self.num_nodes)
+
+    @classmethod
+    def get(cls, rowptr: torch.Tensor, col: torch.Tensor) -> "_DeviceGraph":
+        key = (rowptr.data_ptr(), rowptr.numel(), rowptr._version, col.data_ptr(), col.numel(), col._version,
+               torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        g = cls._cache.get(key)
+        if g is None:
+            g = cls(rowptr, col)
+            g._keep = (rowptr, col)
+            cls._cache[key] = g
+            while len(cls._cache) > 8:
+                cls._cache.popitem(last=False)
+        return g
+
+
+def _sampler_sizes(bs: int, sizes: Sequence[int], g: _DeviceGraph) -> SamplerSizes:
+    L = len(sizes)
+    arr = (ctypes.c_int32 * max(L, 1))(*[int(s) for s in sizes])
+    out = SamplerSizes()
+    check(_lib.load().spp_sampler_sizes(int(bs), arr, L, g.num_nodes, g.max_degree, ctypes.byref(out)),
+          "spp_sampler_sizes")
+    return out
+
+
+class _Workspace:
+    """Per-stream scratch of the sampler (hash table, discovery list, scan state, meta block)."""
+
+    def __init__(self, sz: SamplerSizes, device: torch.device):
+        self.max_nodes = int(sz.max_nodes)
+        self.max_targets = int(sz.max_targets)
+        self.table = torch.empty(int(sz.table_slots), dtype=torch.int64, device=device)
+        self.n_ids = torch.empty(self.max_nodes, dtype=torch.int32, device=device)
+        self.tgt_start = torch.empty(self.max_targets, dtype=torch.int64, device=device)
+        self.tgt_deg = torch.empty(self.max_targets, dtype=torch.int32, device=device)
+        self.tile_state = torch.empty(int(sz.tile_words), dtype=torch.int64, device=device)
+        self.meta = torch.zeros(SPP_META_WORDS, dtype=torch.int64, device=device)
+        self._refresh()
+
+    def _refresh(self):
+        self.c = SamplerWs(self.table.data_ptr(), self.table.numel(), self.n_ids.data_ptr(), self.max_nodes,
+                           self.tgt_start.data_ptr(), self.tgt_deg.data_ptr(), self.max_targets,
+                           self.tile_state.data_ptr(), self.tile_state.numel(), self.meta.data_ptr())
+
+    def ensure_tiles(self, items: int):
+        words = 2 + (max(items, 1) + 1023) // 1024 + 30
+        if words > self.tile_state.numel():
+            self.tile_state = torch.empty(words, dtype=torch.int64, device=self.table.device)
+            self._refresh()
+
+    def meta_ptr(self, word: int) -> int:
+        return self.meta.data_ptr() + 8 * word
+
+
+Adj = Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Tuple[int, int]]
+
+
+def _sample_fused(g: _DeviceGraph, ws: _Workspace, sz: SamplerSizes, seeds_ptr: int, bs: int,
+                  sizes: Sequence[int], replace: bool, rng_seed: int, stream_ptr: int, device,
+                  want_nid: bool):
+    """All hops sampled (fanout >= 0): one C call, no host synchronisation.  Output tensors are
+    allocated at their upper bounds; the exact sizes arrive later through the meta block."""
+    L = len(sizes)
+    rowptrs = [torch.empty(int(sz.hop_targets[h]) + 1, dtype=torch.int64, device=device) for h in range(L)]
+    cols = [torch.empty(max(int(sz.hop_edges[h]), 1), dtype=torch.int64, device=device) for h in range(L)]
+    n_id = torch.empty(ws.max_nodes, dtype=torch.int64, device=device) if want_nid else None
+    rp = (c_vp * max(L, 1))(*[t.data_ptr() for t in rowptrs])
+    cp = (c_vp * max(L, 1))(*[t.data_ptr() for t in cols])
+    caps = (ctypes.c_int64 * max(L, 1))(*[int(sz.hop_edges[h]) for h in range(L)])
+    sz_arr = (ctypes.c_int32 * max(L, 1))(*[int(s) for s in sizes])
+    check(_lib.load().spp_sample_minibatch(ctypes.byref(g.c), seeds_ptr, bs, sz_arr, L, int(bool(replace)),
+                                           ctypes.c_uint64(rng_seed & 0xFFFFFFFFFFFFFFFF), ctypes.byref(ws.c),
+                                           rp, cp, caps, n_id.data_ptr() if want_nid else None, stream_ptr),
+          "spp_sample_minibatch")
+    return rowptrs, cols, n_id
+
+
+def _finish_fused(meta_host: torch.Tensor, rowptrs, cols, L: int) -> Tuple[int, List[Adj]]:
+    """Cut the upper-bound buffers down to the sizes in the (host copy of the) meta block; the
+    adjacency list is reversed like fast_sampler.cpp:224."""
+    m = meta_host.tolist()
+    if m[META_OVERFLOW]:
+        raise SalientB200Error("sampler buffer bound exceeded on the device (SPP_META_OVERFLOW)")
+    adjs: List[Adj] = []
+    for h in range(L):
+        T, E, S = m[h], m[META_EDGES0 + h], m[h + 1]
+        e_id = torch.empty(0, dtype=torch.int64, device=rowptrs[h].device)
+        adjs.append((rowptrs[h][:T + 1], cols[h][:E], e_id, (T, S)))
+    adjs.reverse()
+    return m[L], adjs
+
+
+def _sample_stepwise(g: _DeviceGraph, ws: _Workspace, seeds: torch.Tensor, sizes: Sequence[int], replace: bool,
+                     rng_seed: int, device) -> Tuple[int, List[Adj]]:
+    """Hops whose edge count is data dependent (full neighbourhood): count -> read E -> allocate
+    -> fill, one host synchronisation per phase (the layer-wise inference path)."""
+    L = _lib.load()
+    sp = _stream_ptr()
+    bs = seeds.numel()
+    check(L.spp_sample_begin(ctypes.byref(g.c), seeds.data_ptr(), bs, ctypes.byref(ws.c), sp), "spp_sample_begin")
+    T = bs
+    adjs: List[Adj] = []
+    for h, k in enumerate(sizes):
+        k = int(k)
+        ws.ensure_tiles(T)
+        rowptr = torch.empty(T + 1, dtype=torch.int64, device=device)
+        check(L.spp_sample_hop_count(ctypes.byref(g.c), h, k, int(bool(replace)), T, ctypes.byref(ws.c),
+                                     rowptr.data_ptr(), sp), "spp_sample_hop_count")
+        E = int(ws.meta[META_EDGES0 + h].item())
+        if T + E >= 2 ** 32 - 16:
+            raise SalientB200Error(f"hop {h}: {T}+{E} candidates exceed the 32-bit position range")
+        ws.ensure_tiles(E)
+        col = torch.empty(max(E, 1), dtype=torch.int64, device=device)
+        check(L.spp_sample_hop_fill(ctypes.byref(g.c), h, k, int(bool(replace)),
+                                    ctypes.c_uint64(rng_seed & 0xFFFFFFFFFFFFFFFF), T, E, ctypes.byref(ws.c),
+                                    rowptr.data_ptr(), col.data_ptr(), sp), "spp_sample_hop_fill")
+        meta = ws.meta.tolist()
+        if meta[META_OVERFLOW]:
+            raise SalientB200Error("sampler buffer bound exceeded on the device (SPP_META_OVERFLOW)")
+        S = meta[h + 1]
+        adjs.append((rowptr, col[:E], torch.empty(0, dtype=torch.int64, device=device), (T, S)))
+        T = S
+    adjs.reverse()
+    return T, adjs
+
+
+_free_call_counter = [5489]
+
+
+def _next_free_seed() -> int:
+    _free_call_counter[0] += 1
+    return _free_call_counter[0]
+
+
+def _sample(rowptr, col, idx, sizes: Sequence[int], replace: bool, seed: Optional[int]):
+    device = _device()
+    if len(sizes) > SPP_MAX_HOPS:
+        raise RuntimeError(f"at most {SPP_MAX_HOPS} hops are supported")
+    g = _DeviceGraph.get(rowptr, col)
+    seeds = idx.to(device=device, dtype=torch.int64).contiguous()
+    sz = _sampler_sizes(seeds.numel(), sizes, g)
+    ws = _Workspace(sz, device)
+    rng_seed = _next_free_seed() if seed is None else int(seed)
+    if any(int(s) < 0 for s in sizes):
+        nb, adjs = _sample_stepwise(g, ws, seeds, sizes, replace, rng_seed, device)
+    else:
+        rowptrs, cols, _ = _sample_fused(g, ws, sz, seeds.data_ptr(), seeds.numel(), sizes, replace, rng_seed,
+                                         _stream_ptr(), device, False)
+        nb, adjs = _finish_fused(ws.meta.cpu(), rowptrs, cols, len(sizes))
+    return g, ws, nb, adjs
+
+
+def sample_adj(rowptr: torch.Tensor, col: torch.Tensor, idx: torch.Tensor, num_neighbors: int, replace: bool,
+               pin_memory: bool = False, *, seed: Optional[int] = None):
+    """``fast_sampler.sample_adj`` (fast_sampler/sample_cpu.hpp:154-165, bound at
+    fast_sampler.cpp:1339-1344): one hop; returns ``(rowptr, col, n_id int32, e_id)``."""
+    _, ws, nb, adjs = _sample(rowptr, col, idx, [int(num_neighbors)], bool(replace), seed)
+    rp, cl, e_id, _ = adjs[0]
+    return rp, cl, ws.n_ids[:nb].clone(), e_id
+
+
+def multilayer_sample(idx: torch.Tensor, sizes: Sequence[int], rowptr: torch.Tensor, col: torch.Tensor,
+                      pin_memory: bool = False, *, seed: Optional[int] = None):
+    """``fast_sampler.multilayer_sample`` (fast_sampler/fast_sampler.cpp:229-236, bound at
+    :1345-1350): returns ``(n_id int64, [(rowptr, col, e_id, (T, S)) ...])``, outermost hop first."""
+    _, ws, nb, adjs = _sample(rowptr, col, idx, list(sizes), False, seed)
+    return ws.n_ids[:nb].to(torch.int64), adjs
+
+
+def serial_index(input: torch.Tensor, idx: torch.Tensor, n: Optional[int] = None, pin_memory: bool = False):
+    """``fast_sampler.serial_index`` (fast_sampler/fast_sampler.cpp:238-279): ``out[i] = in[idx[i]]``
+    for ``i < min(len(idx), n)``; rows past ``len(idx)`` are left uninitialised like the reference."""
+    if isinstance(n, bool):  # serial_index(in, idx, pin_memory) overload
+        pin_memory, n = n, None
+    if not ((input.dim() == 2 and input.stride(-1) == 1) or input.size(-1) == 1):
+        raise RuntimeError("input must be 2D row-major tensor")
+    device = _device()
+    table = _resident(input, None, "table")
+    ids = idx.to(device=device)
+    if ids.dtype not in (torch.int64, torch.int32):
+        ids = ids.to(torch.int64)
+    ids = ids.contiguous()
+    n = ids.numel() if n is None else int(n)
+    f = input.size(-1)
+    out = torch.empty((n, f), dtype=input.dtype, device=device)
+    row_bytes = f * input.element_size()
+    if n > 0 and ids.numel() > 0 and row_bytes > 0:
+        check(_lib.load().spp_gather_rows(table.data_ptr(), row_bytes, ids.data_ptr(), int(ids.dtype == torch.int64),
+                                          ids.numel(), None, out.data_ptr(), n, _stream_ptr()), "spp_gather_rows")
+    return out
+
+
+def to_row_major(t: torch.Tensor) -> torch.Tensor:
+    """``fast_sampler.to_row_major`` (fast_sampler/fast_sampler.cpp:281-308).  Set-up-time layout
+    conversion, done by the framework's strided copy."""
+    if t.dim() != 2:
+        raise RuntimeError("only support 2D tensors")
+    tr, tc = t.shape
+    if t.stride(0) == tc and t.stride(1) == 1:
+        return t
+    if not (t.stride(0) == 1 and t.stride(1) == tr):
+        raise RuntimeError("input has unrecognizable stides")
+    return t.contiguous()
+
+
+def full_sample(*args, **kwargs):
+    """``fast_sampler.full_sample`` (fast_sampler/fast_sampler.cpp:310-366).  Its only caller in the
+    reference (FastPreSampler, fast_trainer/samplers.py:402-423) is broken; kept as a stub."""
+    raise SalientB200Error("full_sample is not part of the mini-batch generation path (SURVEY.md section 2, #9)")
+
+
+# ------------------------------------------------------------------------------------------------
+# RangePartitionBook / Cache
+# ------------------------------------------------------------------------------------------------
+def _offsets_host(partition_offsets: torch.Tensor):
+    off = [int(v) for v in partition_offsets.tolist()]
+    if len(off) < 2 or len(off) - 1 > SPP_MAX_PARTS:
+        raise RuntimeError(f"partition_offsets must hold between 2 and {SPP_MAX_PARTS + 1} entries")
+    return off, (ctypes.c_int64 * (SPP_MAX_PARTS + 1))(*(off + [off[-1]] * (SPP_MAX_PARTS + 1 - len(off))))
+
+
+class RangePartitionBook:
+    """``fast_sampler.RangePartitionBook`` (fast_sampler/range_partition_book.hpp:31-57,
+    .cpp:85-112; bound at fast_sampler.cpp:1368-1382)."""
+
+    def __init__(self, rank: int, world_size: int, partition_offsets: torch.Tensor):
+        self.rank = int(rank)
+        self.world_size = int(world_size)
+        self.partition_offsets = partition_offsets
+
+    def _off(self):
+        return _offsets_host(self.partition_offsets)
+
+    def _apply(self, nids: torch.Tensor, fn, out_dtype):
+        device = _device()
+        ids = nids.to(device=device, dtype=torch.int64).contiguous()
+        out = torch.empty(ids.shape, dtype=out_dtype, device=device)
+        fn(ids, out)
+        return out if nids.is_cuda else out.cpu()
+
+    def nid2localnid(self, nids: torch.Tensor, partition_idx: int) -> torch.Tensor:
+        off, arr = self._off()
+        P = len(off) - 1
+        return self._apply(nids, lambda i, o: check(_lib.load().spp_nid2localnid(
+            arr, P, int(partition_idx), i.data_ptr(), i.numel(), o.data_ptr(), _stream_ptr()), "spp_nid2localnid"),
+            torch.int64)
+
+    def nid2partid(self, nids: torch.Tensor) -> torch.Tensor:
+        off, arr = self._off()
+        P = len(off) - 1
+        return self._apply(nids, lambda i, o: check(_lib.load().spp_nid2partid(
+            arr, P, i.data_ptr(), i.numel(), o.data_ptr(), _stream_ptr()), "spp_nid2partid"), torch.int64)
+
+    def nid_is_local(self, nids: torch.Tensor) -> torch.Tensor:
+        off, arr = self._off()
+        P = len(off) - 1
+        return self._apply(nids, lambda i, o: check(_lib.load().spp_nid_is_local(
+            arr, P, self.rank, i.data_ptr(), i.numel(), o.data_ptr(), _stream_ptr()), "spp_nid_is_local"),
+            torch.bool)
+
+    def partid2nids(self, partition_idx: int) -> torch.Tensor:
+        off, _ = self._off()
+        return torch.arange(off[partition_idx], off[partition_idx + 1], dtype=torch.int64)
+
+
+class Cache:
+    """``fast_sampler.Cache`` (fast_sampler/range_partition_book.hpp:60-91, .cpp:116-195; bound at
+    fast_sampler.cpp:1383-1394).  The dense id -> cache-row map lives in HBM (int32[num_nodes],
+    -1 = not cached); it is sized on demand instead of the reference's fixed 200 M entries."""
+
+    def __init__(self, rank: int = 0, world_size: int = 0, cached_vertices: Optional[torch.Tensor] = None,
+                 cached_features: Optional[torch.Tensor] = None):
+        self._rank = int(rank)
+        self._world_size = int(world_size)
+        self._cached_vertices = (cached_vertices if cached_vertices is not None
+                                 else torch.empty(0, dtype=torch.int64))
+        self._cached_features = (cached_features if cached_features is not None
+                                 else torch.empty((0, 0), dtype=torch.float16))
+        self._map: Optional[torch.Tensor] = None
+
+    rank = property(lambda self: self._rank)
+    world_size = property(lambda self: self._world_size)
+    cached_vertices = property(lambda self: self._cached_vertices)
+    cached_features = property(lambda self: self._cached_features)
+
+    def device_map(self, num_nodes: int) -> torch.Tensor:
+        if self._map is None or self._map.numel() < num_nodes:
+            device = _device()
+            cv = self._cached_vertices.to(device=device, dtype=torch.int64).contiguous()
+            if cv.numel() > 0:
+                num_nodes = max(num_nodes, int(cv.max().item()) + 1)
+            m = torch.empty(max(num_nodes, 1), dtype=torch.int32, device=device)
+            check(_lib.load().spp_cache_build_map(cv.data_ptr(), cv.numel(), m.data_ptr(), m.numel(), _stream_ptr()),
+                  "spp_cache_build_map")
+            self._map = m
+        return self._map
+
+    def device_features(self) -> torch.Tensor:
+        return _resident(self._cached_features, None, "cache_features")
+
+    def _lookup(self, nids: torch.Tensor, fn, dtype):
+        device = _device()
+        ids = nids.to(device=device, dtype=torch.int64).contiguous()
+        need = int(ids.max().item()) + 1 if ids.numel() else 1
+        m = self.device_map(need)
+        out = torch.empty(ids.shape, dtype=dtype, device=device)
+        check(fn(m.data_ptr(), ids.data_ptr(), ids.numel(), out.data_ptr(), _stream_ptr()), "cache lookup")
+        return out if nids.is_cuda else out.cpu()
+
+    def nid_is_cached(self, nids: torch.Tensor) -> torch.Tensor:
+        return self._lookup(nids, _lib.load().spp_nid_is_cached, torch.bool)
+
+    def nid2cachenid(self, nids: torch.Tensor) -> torch.Tensor:
+        return self._lookup(nids, _lib.load().spp_nid2cachenid, torch.int64)
+
+
+def make_feature_map(offsets: Sequence[int], rank: int, tables: Sequence[Optional[torch.Tensor]],
+                     cache_table: Optional[torch.Tensor] = None, cache_map: Optional[torch.Tensor] = None,
+                     table_ptrs: Optional[Sequence[int]] = None) -> FeatureMap:
+    """Fill the C ``spp_feature_map``: ``tables[p]`` are device tensors (local partitions) and/or
+    ``table_ptrs[p]`` raw device pointers of IPC-mapped peer partitions."""
+    P = len(offsets) - 1
+    fm = FeatureMap()
+    fm.num_parts = P
+    fm.rank = int(rank)
+    for p in range(SPP_MAX_PARTS + 1):
+        fm.offsets[p] = int(offsets[min(p, P)])
+    for p in range(P):
+        ptr = None
+        if table_ptrs is not None and table_ptrs[p]:
+            ptr = int(table_ptrs[p])
+        elif tables is not None and tables[p] is not None and tables[p].numel() > 0:
+            ptr = tables[p].data_ptr()
+        fm.tables[p] = ptr
+    fm.cache_table = cache_table.data_ptr() if cache_table is not None and cache_table.numel() > 0 else None
+    fm.cache_map = cache_map.data_ptr() if (cache_map is not None and fm.cache_table) else None
+    return fm
+
+
+# ------------------------------------------------------------------------------------------------
+# Config / ProtoDistributedBatch / Session
+# ------------------------------------------------------------------------------------------------
+class Config:
+    """``fast_sampler.Config`` (fast_sampler/fast_sampler.cpp:515-531,1290-1309): default
+    constructible, read-write fields.  ``partition_tables`` / ``peer_table_ptrs`` are optional
+    extensions: per-partition feature tables reachable from this GPU (local tensors or
+    IPC-mapped peer pointers); when absent in distributed mode they are exchanged over
+    ``torch.distributed`` by :mod:`salient_plusplus_b200.peer`."""
+
+    def __init__(self):
+        self.x_cpu = torch.empty((0, 0))
+        self.x_gpu = torch.empty((0, 0))
+        self.y = None
+        self.rowptr = torch.zeros(1, dtype=torch.int64)
+        self.col = torch.empty(0, dtype=torch.int64)
+        self.idx = torch.empty(0, dtype=torch.int64)
+        self.batch_size = 0
+        self.sizes: List[int] = []
+        self.skip_nonfull_batch = False
+        self.pin_memory = False
+        self.distributed = False
+        self.partition_book: Optional[RangePartitionBook] = None
+        self.cache: Cache = Cache()
+        self.force_exact_num_batches = False
+        self.exact_num_batches = 0
+        self.count_remote_frequency = False
+        self.use_cache = False
+        # extensions (not in the reference)
+        self.partition_tables = None
+        self.peer_table_ptrs = None
+        self.fused_gather = True
+
+
+class ProtoDistributedBatch:
+    """``fast_sampler.ProtoDistributedBatch`` (fast_sampler/fast_sampler.cpp:180-188,1281-1289).
+    ``n_id`` and ``x`` are extensions: the MFG node list and, when the partition tables are
+    reachable, the features already gathered in MFG order by the fused P2P kernel."""
+
+    def __init__(self):
+        self.partition_nids: List[torch.Tensor] = []
+        self.sliced_cpu_features = None
+        self.sliced_cpu_labels = None
+        self.cached_nids = None
+        self.perm_partition_to_mfg = None
+        self.adjs: List[Adj] = []
+        self.idx_range: Tuple[int, int] = (0, 0)
+        self.n_id = None
+        self.x = None
+
+
+def _batch_ranges(n: int, cfg: Config) -> List[Tuple[int, int]]:
+    """Batch ranges exactly as the reference enqueues them (fast_sampler/fast_sampler.cpp:587-627)."""
+    out: List[Tuple[int, int]] = []
+    if cfg.force_exact_num_batches:
+        B = int(cfg.exact_num_batches)
+        if B <= 0:
+            raise RuntimeError("exact_num_batches must be positive")
+        avg = n // B - 1
+        if avg < 0:
+            raise RuntimeError("force_exact_num_batches: fewer seeds than batches")
+        sizes = [avg] * B
+        rem = n - avg * B
+        i = 0
+        while rem > 0:
+            sizes[i % B] += 1
+            rem -= 1
+            i += 1
+        s = 0
+        for b in sizes:
+            out.append((s, s + b))
+            s += b
+    else:
+        bs = int(cfg.batch_size)
+        if bs <= 0:
+            raise RuntimeError("batch_size must be positive")
+        for i in range(0, n, bs):
+            this = min(n, i + bs) - i
+            if cfg.skip_nonfull_batch and this < bs:
+                continue
+            out.append((i, i + this))
+    return out
+
+
+class _Slot:
+    def __init__(self, ws: _Workspace, device, extra_words: int):
+        self.ws = ws
+        self.stream = torch.cuda.Stream(device)
+        self.event = torch.cuda.Event()
+        self.meta_host = torch.empty(SPP_META_WORDS + extra_words, dtype=torch.int64).pin_memory()
+        self.job = None
+
+
+class Session:
+    """``fast_sampler.Session`` (fast_sampler/fast_sampler.cpp:533-936, bound at :1310-1338)."""
+
+    def __init__(self, num_threads: int, max_items_in_queue: int, config: Config):
+        if max_items_in_queue <= 0:
+            raise RuntimeError(f"max_items_in_queue ({max_items_in_queue}) must be positive")
+        self._config = copy.copy(config)  # copied by value like fast_sampler.cpp:541-542
+        cfg = self._config
+        self._device = _device()
+        self._lib = _lib.load()
+        self._sizes = [int(s) for s in cfg.sizes]
+        if len(self._sizes) > SPP_MAX_HOPS:
+            raise RuntimeError(f"at most {SPP_MAX_HOPS} hops are supported")
+        self._g = _DeviceGraph.get(cfg.rowptr, cfg.col)
+        self._idx = cfg.idx.to(device=self._device, dtype=torch.int64).contiguous()
+        self._ranges = _batch_ranges(self._idx.numel(), cfg)
+        self._num_total = len(self._ranges)
+        self._num_consumed = 0
+        self._next = 0
+        self.total_blocked_dur = datetime.timedelta(0)
+        self.total_blocked_occasions = 0
+        self._full = any(s < 0 for s in self._sizes)
+        self._y = _resident(cfg.y, None, "y") if cfg.y is not None else None
+        if self._y is not None and self._y.dim() == 1:
+            self._y = self._y.view(-1, 1)
+        self._setup_features()
+        max_bs = max((e - s for s, e in self._ranges), default=0)
+        self._sz = _sampler_sizes(max_bs, self._sizes, self._g)
+        depth = int(os.environ.get("SPP_SESSION_DEPTH", "4"))
+        depth = max(1, min(depth, int(max_items_in_queue), max(self._num_total, 1)))
+        P = self._P if cfg.distributed else 0
+        self._slots = [_Slot(_Workspace(self._sz, self._device), self._device, SPP_MAX_PARTS + 2)
+                       for _ in range(depth)]
+        if cfg.distributed:
+            words = int(self._lib.spp_split_scratch_words(self._sz.max_nodes))
+            for s in self._slots:
+                s.split_scratch = torch.empty(words, dtype=torch.int32, device=self._device)
+                s.counts = torch.zeros(SPP_MAX_PARTS + 2, dtype=torch.int64, device=self._device)
+        self._free = deque(self._slots)
+        self._pending: deque = deque()
+        self._freq = None
+        self._freq_reduced = False
+        self.remote_frequency_tensor = torch.empty(0, dtype=torch.int64)
+        self.remote_vertices_ordered_by_freq = torch.empty(0, dtype=torch.int64)
+        self._slice_result = None
+        # the side streams must see set-up work (uploads, cache map) issued on the current stream
+        cur = torch.cuda.current_stream()
+        for s in self._slots:
+            s.stream.wait_stream(cur)
+        while self._free and self._next < self._num_total:
+            self._enqueue()
+
+    # -- set-up -------------------------------------------------------------------------------
+    def _setup_features(self):
+        cfg = self._config
+        self._fm = None
+        self._x_table = None
+        self._x_cpu_dev = None
+        if not cfg.distributed:
+            x = cfg.x_cpu
+            if x is not None and x.dim() == 2 and x.numel() > 0:
+                self._x_table = _resident(x, None, "x")
+            self._feat_shape = (x.size(-1), x.dtype) if x is not None and x.dim() == 2 else (0, torch.float16)
+            return
+        book = cfg.partition_book
+        if book is None:
+            raise RuntimeError("distributed Session needs a partition_book")
+        off, _ = _offsets_host(book.partition_offsets)
+        self._off = off
+        self._P = len(off) - 1
+        self._rank = int(book.rank)
+        if not (0 <= self._rank < self._P):
+            raise RuntimeError("partition_book.rank out of range")
+        xg = cfg.x_gpu if cfg.x_gpu is not None else torch.empty((0, 0))
+        xc = cfg.x_cpu if cfg.x_cpu is not None else torch.empty((0, 0))
+        self._x_gpu_rows = xg.size(0) if xg.dim() == 2 else 0
+        has_g = xg.dim() == 2 and xg.numel() > 0
+        has_c = xc.dim() == 2 and xc.numel() > 0
+        if has_c:
+            self._x_cpu_dev = _resident(xc, None, "x_cpu")
+        if has_g and has_c:
+            key = ("xlocal", xg.data_ptr(), xc.data_ptr(), xg.size(0), xc.size(0))
+            hit = _RESIDENT.get(key)
+            if hit is None:
+                local = torch.cat([_resident(xg, None, "x_gpu"), self._x_cpu_dev], dim=0)
+                _RESIDENT[key] = ((xg, xc), local)
+            else:
+                local = hit[1]
+        elif has_g:
+            local = _resident(xg, None, "x_gpu")
+        elif has_c:
+            local = self._x_cpu_dev
+        else:
+            local = None
+        self._x_local = local
+        ref = xg if has_g else xc
+        self._feat_shape = (ref.size(-1), ref.dtype) if ref.dim() == 2 else (0, torch.float16)
+        self._use_cache = bool(cfg.use_cache)
+        self._cache_map = cfg.cache.device_map(self._g.num_nodes) if self._use_cache else None
+        self._cache_feats = cfg.cache.device_features() if self._use_cache else None
+        # book-only map for the split kernel
+        self._split_fm = make_feature_map(off, self._rank, [None] * self._P)
+        if self._use_cache:
+            self._split_fm.cache_map = self._cache_map.data_ptr()
+        # full map (tables of every partition) for the fused gather, when reachable
+        if cfg.fused_gather and local is not None:
+            tables = [None] * self._P
+            ptrs = [0] * self._P
+            if cfg.partition_tables is not None:
+                tables = [(_resident(t, None, f"part{p}") if t is not None else None)
+                          for p, t in enumerate(cfg.partition_tables)]
+            if cfg.peer_table_ptrs is not None:
+                ptrs = [int(v or 0) for v in cfg.peer_table_ptrs]
+            tables[self._rank] = local
+            ptrs[self._rank] = 0
+            reachable = all((tables[p] is not None) or ptrs[p] or off[p + 1] == off[p] for p in range(self._P))
+            if not reachable:
+                from . import peer
+                got = peer.exchange_partition_tables(local, self._rank, self._P)
+                if got is not None:
+                    ptrs = got
+                    ptrs[self._rank] = 0
+                    reachable = True
+            if reachable:
+                self._part_tables = tables  # keep alive
+                self._fm = make_feature_map(off, self._rank, tables, self._cache_feats, self._cache_map, ptrs)
+
+    # -- enqueue / finalise ---------------------------------------------------------------------
+    def _enqueue(self):
+        slot = self._free.popleft()
+        start, stop = self._ranges[self._next]
+        self._next += 1
+        bs = stop - start
+        cfg = self._config
+        rng_seed = (stop * 17 + 5) & 0xFFFFFFFF  # fast_sampler.cpp:994
+        seeds_ptr = self._idx.data_ptr() + 8 * start
+        L = len(self._sizes)
+        job = {"range": (start, stop), "bs": bs}
+        with torch.cuda.stream(slot.stream):
+            sp = slot.stream.cuda_stream
+            ws = slot.ws
+            if self._full:
+                nb, adjs = _sample_stepwise(self._g, ws, self._idx[start:stop], self._sizes, False, rng_seed,
+                                            self._device)
+                job["ready"] = (nb, adjs)
+            else:
+                job["rowptrs"], job["cols"], n_id = _sample_fused(
+                    self._g, ws, self._sz, seeds_ptr, bs, self._sizes, False, rng_seed, sp, self._device,
+                    cfg.distributed)
+                job["n_id"] = n_id
+            n_dev = ws.meta_ptr(L)
+            fdim, fdtype = self._feat_shape
+            row_bytes = fdim * torch.empty(0, dtype=fdtype).element_size()
+            if not cfg.distributed:
+                if self._x_table is not None:
+                    x = torch.empty((ws.max_nodes, fdim), dtype=fdtype, device=self._device)
+                    check(self._lib.spp_gather_rows(self._x_table.data_ptr(), row_bytes, ws.n_ids.data_ptr(), 0,
+                                                    ws.max_nodes, n_dev, x.data_ptr(), ws.max_nodes, sp),
+                          "spp_gather_rows")
+                else:
+                    x = torch.empty((0, fdim), dtype=fdtype, device=self._device)
+                job["x"] = x
+            else:
+                if self._full:
+                    n_id = torch.empty(ws.max_nodes, dtype=torch.int64, device=self._device)
+                    check(self._lib.spp_sample_export_nids(ctypes.byref(ws.c), L, n_id.data_ptr(), 1, ws.max_nodes, sp),
+                          "spp_sample_export_nids")
+                    job["n_id"] = n_id
+                bucket_ids = torch.empty(ws.max_nodes, dtype=torch.int64, device=self._device)
+                perm = torch.empty(ws.max_nodes, dtype=torch.int64, device=self._device)
+                check(self._lib.spp_split_by_owner(ctypes.byref(self._split_fm), int(self._use_cache),
+                                                   ws.n_ids.data_ptr(), 0, ws.max_nodes, n_dev, bucket_ids.data_ptr(),
+                                                   perm.data_ptr(), slot.counts.data_ptr(),
+                                                   slot.split_scratch.data_ptr(), sp), "spp_split_by_owner")
+                job["bucket_ids"], job["perm"] = bucket_ids, perm
+                if self._fm is not None:
+                    x = torch.empty((ws.max_nodes, fdim), dtype=fdtype, device=self._device)
+                    check(self._lib.spp_gather_partitioned(ctypes.byref(self._fm), row_bytes, ws.n_ids.data_ptr(), 0,
+                                                           ws.max_nodes, n_dev, x.data_ptr(), ws.max_nodes, None, sp),
+                          "spp_gather_partitioned")
+                    job["x"] = x
+                slot.meta_host[SPP_META_WORDS:].copy_(slot.counts, non_blocking=True)
+            if self._y is not None and bs > 0:
+                y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
+                check(self._lib.spp_gather_rows(self._y.data_ptr(), self._y.size(-1) * self._y.element_size(),
+                                                seeds_ptr, 1, bs, None, y.data_ptr(), bs, sp), "spp_gather_rows(y)")
+                job["y"] = y
+            else:
+                job["y"] = None if self._y is None else torch.empty((0, self._y.size(-1)), dtype=self._y.dtype,
+                                                                     device=self._device)
+            slot.meta_host[:SPP_META_WORDS].copy_(ws.meta, non_blocking=True)
+            slot.event.record(slot.stream)
+        slot.job = job
+        self._pending.append(slot)
+
+    def _finalize(self, slot: _Slot):
+        job = slot.job
+        slot.job = None
+        cfg = self._config
+        L = len(self._sizes)
+        if "ready" in job:
+            nb, adjs = job["ready"]
+        else:
+            nb, adjs = _finish_fused(slot.meta_host[:SPP_META_WORDS], job["rowptrs"], job["cols"], L)
+        start, stop = job["range"]
+        if not cfg.distributed:
+            x = job["x"]
+            out = (x[:nb] if x.size(0) >= nb else x, job["y"], adjs, (start, stop))
+        else:
+            counts = slot.meta_host[SPP_META_WORDS:].tolist()
+            P = self._P
+            b = ProtoDistributedBatch()
+            ids = job["bucket_ids"]
+            pos = 0
+            for p in range(P):
+                b.partition_nids.append(ids[pos:pos + counts[p]])
+                pos += counts[p]
+            b.cached_nids = ids[pos:pos + counts[P]]
+            b.perm_partition_to_mfg = job["perm"][:nb]
+            b.adjs = adjs
+            b.idx_range = (start, stop)
+            b.sliced_cpu_labels = job["y"]
+            b.n_id = job["n_id"][:nb]
+            b.x = job["x"][:nb] if "x" in job else None
+            fdim, fdtype = self._feat_shape
+            if self._x_cpu_dev is not None:
+                # compatibility with gpu_percent < 1 (fast_sampler.cpp:1041-1052,1142-1155): rows of
+                # local nodes whose local id lies in the x_cpu tail, in partition_nids[rank] order
+                loc = b.partition_nids[self._rank] - self._off[self._rank]
+                sel = loc[loc >= self._x_gpu_rows] - self._x_gpu_rows
+                b.sliced_cpu_features = serial_index(self._x_cpu_dev, sel)
+            else:
+                b.sliced_cpu_features = torch.empty((0, fdim), dtype=fdtype, device=self._device)
+            if cfg.count_remote_frequency and not cfg.use_cache:
+                self._count_remote(b)
+            out = b
+        self._num_consumed += 1
+        self._free.append(slot)
+        while self._free and self._next < self._num_total:
+            self._enqueue()
+        return out
+
+    def _count_remote(self, b: ProtoDistributedBatch):
+        # fast_sampler.cpp:1093-1103 (set-up-time statistics for cache_strategy=simulation)
+        if self._freq is None:
+            self._freq = torch.zeros(self._g.num_nodes, dtype=torch.int64, device=self._device)
+        for p in range(self._P):
+            if p != self._rank and b.partition_nids[p].numel():
+                self._freq.index_add_(0, b.partition_nids[p],
+                                      torch.ones_like(b.partition_nids[p]))
+
+    # -- consumer API ---------------------------------------------------------------------------
+    @property
+    def config(self) -> Config:
+        return self._config
+
+    def _get(self, blocking: bool):
+        if self._num_consumed == self._num_total:
+            return None
+        slot = self._pending[0]
+        if not slot.event.query():
+            if not blocking:
+                return None
+            t0 = time.perf_counter()
+            slot.event.synchronize()
+            self.total_blocked_dur += datetime.timedelta(microseconds=int((time.perf_counter() - t0) * 1e6))
+            self.total_blocked_occasions += 1
+        self._pending.popleft()
+        return self._finalize(slot)
+
+    def try_get_batch(self):
+        if self._config.distributed:
+            raise RuntimeError("try_get_batch called on a distributed Session")
+        return self._get(False)
+
+    def blocking_get_batch(self):
+        if self._config.distributed:
+            raise RuntimeError("blocking_get_batch called on a distributed Session")
+        return self._get(True)
+
+    def try_get_batch_distributed(self):
+        if not self._config.distributed:
+            raise RuntimeError("try_get_batch_distributed called on a non-distributed Session")
+        return self._get(False)
+
+    def blocking_get_batch_distributed(self):
+        if not self._config.distributed:
+            raise RuntimeError("blocking_get_batch_distributed called on a non-distributed Session")
+        return self._get(True)
+
+    num_consumed_batches = property(lambda self: self._num_consumed)
+    num_total_batches = property(lambda self: self._num_total)
+    approx_num_complete_batches = property(lambda self: self._num_consumed + sum(
+        1 for s in self._pending if s.event.query()))
+
+    # -- async_slice_tensors (fast_sampler.cpp:720-775): serve other ranks' requests for rows that
+    #    the reference keeps on the host; here those rows are in HBM too -----------------------
+    def async_slice_tensors(self, ids: List[torch.Tensor], my_rank: int):
+        res = []
+        for i, t in enumerate(ids):
+            t = t.to(self._device)
+            cpu_pos = torch.nonzero(t >= 0).view(-1)
+            gpu_pos = torch.nonzero(t < 0).view(-1)
+            if i != my_rank and self._x_cpu_dev is not None:
+                x_s = serial_index(self._x_cpu_dev, t[cpu_pos])
+            elif i != my_rank:
+                fdim, fdtype = self._feat_shape
+                x_s = torch.empty((0, fdim), dtype=fdtype, device=self._device)
+            else:
+                x_s = torch.empty(0, dtype=torch.int64, device=self._device)
+            res.append([x_s, cpu_pos, gpu_pos])
+        self._slice_result = res
+
+    def wait_slice_tensors(self):
+        return None
+
+    def get_slice_tensors(self):
+        return self._slice_result
+
+    # -- remote frequency statistics (fast_sampler.cpp:835-880) -------------------------------------
+    def reduce_multithreaded_frequency_counts(self):
+        if self._freq_reduced:
+            return
+        if self._freq is not None:
+            verts = torch.nonzero(self._freq).view(-1)
+            f = self._freq[verts]
+            order = torch.argsort(f, descending=True, stable=True)
+            self.remote_frequency_tensor = f[order].cpu()
+            self.remote_vertices_ordered_by_freq = verts[order].cpu()
+        self._freq_reduced = True
+
+    def get_n_most_freq_remote_vertices(self, n: int) -> torch.Tensor:
+        self.reduce_multithreaded_frequency_counts()
+        return self.remote_vertices_ordered_by_freq[:n].clone()
