@@ -623,7 +623,7 @@ static int reset_tiles(const spp_sampler_ws* ws, int64_t bound_items, cudaStream
 static int launch_begin(const spp_graph* g, const int64_t* seeds, int64_t bs, const spp_sampler_ws* ws,
                         cudaStream_t st) {
   if (int r = check_ws(ws)) return r;
-  if (!g || !g->rowptr || (!g->col && g->num_nodes > 0)) return fail(SPP_EINVAL, "sampler: null graph");
+  if (!g || !g->rowptr) return fail(SPP_EINVAL, "sampler: null graph");  // col may be NULL when nnz == 0
   if (bs < 0 || bs > ws->max_nodes) return fail(SPP_ECAPACITY, "sampler: batch_size %lld exceeds max_nodes %lld",
                                                  (long long)bs, (long long)ws->max_nodes);
   if (bs > 0 && !seeds) return fail(SPP_EINVAL, "sampler: null seeds");
