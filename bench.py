@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py -- sampled-and-gathered mini-batches/s (+ gathered feature GB/s) of the mini-batch
+generation path, on synthetic graphs of the BASELINE shapes.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this framework
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU sampler
+
+A "step" is one mini-batch: 1024 seeds -> 3-hop (15,10,5) neighbour sampling with dedup/relabel
+-> feature gather of every sampled node (+ label gather).  At N=1 the workload is BASELINE.json
+configs[1] (ogbn-products-shaped, 100-d fp16).  At N>1 (torchrun, one rank per GPU) the graph
+is replicated, the features are range-partitioned N ways with a replicated hot-vertex cache and
+the rows of other partitions are read over NVLink by the fused P2P gather (weak scaling: every
+rank runs K batches).
+
+Printed JSON (rank 0, one line): see the contract in the task statement; `value` is the
+device-timed throughput with every input resident in HBM, `e2e` goes through the public
+FastSampler/DevicePrefetcher API with the seeds in pinned host memory (H2D of the seeds and
+D2H of the batch's size block inside the timed region, every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (dataset shape, fanout, batch, description)
+    "products": ("products", [15, 10, 5], 1024,
+                 "ogbn-products-shaped synthetic (2.45M nodes, 61.9M directed edges symmetrised, 100-d fp16), "
+                 "fanout (15,10,5), batch 1024"),
+    "arxiv": ("arxiv", [15, 10, 5], 1024,
+              "ogbn-arxiv-shaped synthetic (169K nodes, 1.17M directed edges symmetrised, 128-d fp32), "
+              "fanout (15,10,5), batch 1024"),
+    "papers100M": ("papers100M", [15, 10, 5], 1024,
+                   "ogbn-papers100M-shaped synthetic (111M nodes, 1.6B directed edges, 128-d fp16), fanout (15,10,5)"),
+}
+METRIC = "sampled_and_gathered_minibatches_per_sec"
+UNIT = "batches/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_graph(shape: str, scale: float, device):
+    from salient_plusplus_b200 import synthetic as S
+    n, e, f, dt = S.SHAPES[shape]
+    n, e = max(1024, int(n * scale)), max(4096, int(e * scale))
+    rowptr, col = S.powerlaw_graph(n, e, seed=1, device=device)
+    return n, f, dt, rowptr, col
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the box's host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference_cpu(rowptr, col, x, y, idx, sizes, bs, threads, warmup, steps, max_seconds=None):
+    """Drain a reference fast_sampler.Session (oracle/_ref, built from /root/reference by
+    oracle/build_ref.sh).  Returns (batches/s, gathered GB/s, batches timed, kind)."""
+    from oracle import ref
+    os.environ.setdefault("OMP_NUM_THREADS", "1")  # utils/exp_driver.py:154
+    if ref.available():
+        R = ref.load_reference()
+        cfg = R.Config()
+        cfg.x_cpu, cfg.x_gpu, cfg.y = x, torch.empty(0), y
+        cfg.rowptr, cfg.col, cfg.idx = rowptr, col, idx
+        cfg.batch_size, cfg.sizes = bs, list(sizes)
+        cfg.skip_nonfull_batch = True
+        cfg.pin_memory = bool(torch.cuda.is_available())
+        cfg.distributed = False
+        cfg.force_exact_num_batches, cfg.exact_num_batches = False, 0
+        cfg.count_remote_frequency = cfg.use_cache = False
+        sess = R.Session(threads, 100, cfg)
+        total = sess.num_total_batches
+        got, nodes = 0, 0
+        t0 = None
+        t_start = time.perf_counter()
+        while True:
+            if got == warmup:
+                t0 = time.perf_counter()
+                nodes = 0
+            b = sess.blocking_get_batch()
+            if b is None:
+                break
+            got += 1
+            if got > warmup:
+                nodes += b[0].size(0)
+            if got >= warmup + steps:
+                break
+            if max_seconds is not None and t0 is not None and time.perf_counter() - t0 > max_seconds and got > warmup + 8:
+                break
+        t1 = time.perf_counter()
+        timed = got - warmup
+        # drain so the worker threads go back to the pool cleanly
+        while sess.blocking_get_batch() is not None:
+            pass
+        del sess
+        dt = t1 - (t0 if t0 is not None else t_start)
+        gbs = nodes * x.size(1) * x.element_size() / dt / 1e9
+        return timed / dt, gbs, timed, "reference", total
+    # fallback: the single-threaded C port (oracle/salient_oracle.c)
+    import ctypes
+    import numpy as np
+    from oracle import oracle as O
+    L = O.lib()
+    rp, cl = rowptr.numpy(), col.numpy()
+    xs = x.view(torch.int16).numpy() if x.dtype == torch.float16 else x.numpy()
+    row_bytes = x.size(1) * x.element_size()
+    out = np.empty((1100000, xs.shape[1]), dtype=xs.dtype)
+    sz = (ctypes.c_int32 * len(sizes))(*sizes)
+    ids = idx.numpy()
+    t0, nodes, timed = None, 0, 0
+    for b in range(warmup + steps):
+        if b == warmup:
+            t0 = time.perf_counter()
+        seeds = np.ascontiguousarray(ids[b * bs:(b + 1) * bs])
+        nb = L.spo_minibatch(rp.ctypes.data, cl.ctypes.data, seeds.ctypes.data, seeds.size, sz, len(sizes),
+                             ((b + 1) * bs * 17 + 5) & 0xFFFFFFFF, xs.ctypes.data, row_bytes, out.ctypes.data,
+                             out.shape[0])
+        if b >= warmup:
+            nodes += nb
+            timed += 1
+            if max_seconds is not None and time.perf_counter() - t0 > max_seconds:
+                break
+    dt = time.perf_counter() - t0
+    return timed / dt, nodes * row_bytes / dt / 1e9, timed, "port", warmup + steps
+
+
+def reference_arm(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from salient_plusplus_b200 import synthetic as S
+    shape, sizes, bs, desc = WORKLOADS[args.workload]
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    n, f, dt, rowptr, col = make_graph(shape, args.scale, dev)
+    rowptr, col = rowptr.cpu(), col.cpu()
+    x = S.features(n, f, dt, seed=2, device=dev).cpu()
+    y = S.labels(n, seed=3)
+    need = (args.warmup + args.steps) * bs
+    idx = S.seeds(n, min(n, need), seed=7)
+    if idx.numel() < need:
+        idx = idx.repeat((need + idx.numel() - 1) // idx.numel())[:need]
+    threads = os.cpu_count() or 1
+    bps, gbs, timed, kind, _ = run_reference_cpu(rowptr, col, x, y, idx, sizes, bs, threads, args.warmup, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(bps, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": timed, "warmup": args.warmup, "ms_per_step": round(1000.0 / bps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": desc, "graph_generator": "Chung-Lu power law gamma=2.5 head_offset=100 seed=1",
+                   "scale": args.scale, "nnz": int(col.numel())},
+        "gathered_GBps": round(gbs, 3),
+        "cpu_baseline": {"value": round(bps, 3), "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{timed} mini-batches after {args.warmup} warm-up, reference fast_sampler.Session "
+                                   f"with {threads} worker threads (sampling + CPU feature slice, pinned outputs)"},
+        "e2e": {"value": round(bps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this framework
+# ------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from salient_plusplus_b200 import _lib, fast_sampler as fs, synthetic as S
+    from salient_plusplus_b200.pipeline import MiniBatchPipeline
+    from salient_plusplus_b200.samplers import FastSampler, FastSamplerConfig
+    from salient_plusplus_b200.transferers import DeviceDistributedPrefetcher, DevicePrefetcher
+    lib = _lib.load()
+
+    shape, sizes, bs, desc = WORKLOADS[args.workload]
+    K, W = args.steps, args.warmup
+    n, f, dt, rowptr, col = make_graph(shape, args.scale, dev)
+    col32 = col.to(torch.int32)
+    x_full = S.features(n, f, dt, seed=2, device=dev)
+    y = S.labels(n, seed=3, device=dev)
+    row_bytes = f * x_full.element_size()
+
+    P = world
+    off = S.equal_partition_offsets(n, P)
+    lo, hi = int(off[rank]), int(off[rank + 1])
+    need = (W + K) * bs
+    idx = S.seeds(n, min(hi - lo, need), seed=7 + rank, device=dev, lo=lo, hi=hi)  # federated: local seeds
+    if idx.numel() < need:
+        idx = idx.repeat((need + idx.numel() - 1) // idx.numel())[:need]
+    idx_host = idx.cpu().pin_memory()
+
+    fm = None
+    cache = fs.Cache()
+    x_local = x_full
+    cache_rows = 0
+    if P > 1:
+        x_local = x_full[lo:hi].clone()
+        cache_rows = int((n / P) * args.cache_pct / 100.0)
+        cv = S.degree_cache_vertices(rowptr, off.to(dev), rank, cache_rows)
+        cache = fs.Cache(rank, P, cv, x_full[cv].contiguous())
+        del x_full
+        torch.cuda.empty_cache()
+        from salient_plusplus_b200 import peer
+        ptrs = peer.exchange_partition_tables(x_local, rank, P)
+        ptrs[rank] = 0
+        tables = [None] * P
+        tables[rank] = x_local
+        fm = fs.make_feature_map(off.tolist(), rank, tables, cache.device_features(), cache.device_map(n), ptrs)
+
+    pipe = MiniBatchPipeline(rowptr, col32, sizes, bs, x_table=None if fm is not None else x_local, y_table=y,
+                             feature_map=fm, feat_dim=f, feat_dtype=dt, split=False, depth=args.depth, device=dev)
+    D = len(pipe.slots)
+    main = torch.cuda.current_stream()
+
+    def seed_ptr(b):
+        return idx.data_ptr() + 8 * b * bs
+
+    def run_batches(first, count, time_gather=False, single_stream=False):
+        evs = []
+        for i in range(count):
+            b = first + i
+            ev = pipe.launch(0 if single_stream else b % D, seed_ptr(b), bs, ((b + 1) * bs * 17 + 5) & 0xFFFFFFFF,
+                             time_gather)
+            if ev:
+                evs.append((b, ev))
+        return evs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-timed, inputs resident in HBM -------------------------------------------
+    run_batches(0, W)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = lib.spp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for s in pipe.slots:
+        s.stream.wait_event(e0)
+    run_batches(W, K)
+    for s in pipe.slots:
+        main.wait_stream(s.stream)
+    e1.record(main)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.spp_launch_count() - launches0)
+    clk = clocks.stop()
+
+    # ---- roofline pass: the feature gather timed with CUDA events on its own stream -----------
+    evs = run_batches(W, min(K, 64), time_gather=True, single_stream=True)
+    torch.cuda.synchronize()
+    g_ms, g_bytes, nodes_total = 0.0, 0, 0
+    # N_b of every batch of the pass: re-sample is deterministic, so read N_b batch by batch
+    for b, ev in evs:
+        g_ms += ev[0].elapsed_time(ev[1])
+    for b, _ in evs[:8]:
+        pipe.launch(0, seed_ptr(b), bs, ((b + 1) * bs * 17 + 5) & 0xFFFFFFFF)
+        nodes_total += pipe.read_meta(0)[len(sizes)]
+    mean_nodes = nodes_total / max(1, min(8, len(evs)))
+    idx_bytes = 4  # the gather reads the sampler's int32 node list
+    alg_bytes_per_launch = mean_nodes * (2 * row_bytes + idx_bytes)
+    g_ms_avg = g_ms / max(1, len(evs))
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes_per_launch / (g_ms_avg * 1e-3) / 1e9 if g_ms_avg > 0 else 0.0
+
+    # ---- e2e: public API, seeds in pinned host memory, per-step H2D + D2H ---------------------
+    def make_iter(first, count):
+        cfg = FastSamplerConfig(
+            x_cpu=x_local if P == 1 else torch.empty((0, f), dtype=dt), x_gpu=x_local if P > 1 else torch.empty((0, f), dtype=dt),
+            y=y, rowptr=rowptr, col=col32, idx=idx_host[first * bs:(first + count) * bs], batch_size=bs,
+            sizes=list(sizes), skip_nonfull_batch=False, pin_memory=True, distributed=P > 1,
+            partition_book=fs.RangePartitionBook(rank, P, off) if P > 1 else None, cache=cache,
+            force_exact_num_batches=False, exact_num_batches=0, count_remote_frequency=False, use_cache=P > 1)
+        if P > 1:
+            cfg.peer_table_ptrs = ptrs
+        sampler = FastSampler(16, max(args.depth, 4), cfg)
+        it = iter(sampler)
+        return (DeviceDistributedPrefetcher([dev], it) if P > 1 else DevicePrefetcher([dev], it))
+
+    for _ in make_iter(0, max(W, 3)):
+        pass
+    barrier()
+    prof = None
+    if args.profile_e2e:
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
+    t0 = time.perf_counter()
+    got, e2e_nodes = 0, 0
+    for (batch,) in make_iter(W, K):
+        got += 1
+        e2e_nodes += batch.x.size(0)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(18)
+    if world > 1:
+        t = torch.tensor([ms, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, t_e2e = t.tolist()
+    assert got == K
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the reference fast_sampler on the host cores --
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cb = min(K + W, 96)
+        bps, gbs, timed, kind, _ = run_reference_cpu(rowptr.cpu(), col.cpu(), x_local.cpu(), y.cpu(),
+                                                     idx_host[:(cb + 8) * bs].clone(), sizes, bs, threads, 8, cb,
+                                                     max_seconds=25.0)
+        cpu = {"value": round(bps, 3), "unit": UNIT, "cores": threads, "kind": kind, "gathered_GBps": round(gbs, 3),
+               "sample": f"{timed} mini-batches of the same workload after 8 warm-up, reference fast_sampler.Session, "
+                         f"{threads} worker threads, pinned outputs (sampling + CPU feature slice)"}
+
+    if rank == 0:
+        value = world * K / (ms * 1e-3)
+        e2e_v = world * K / t_e2e
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": desc + (f"; features partitioned {P}-way, {args.cache_pct}% replicated "
+                                           f"degree-ranked cache, P2P gather over NVLink" if P > 1 else ""),
+                       "graph_generator": "Chung-Lu power law gamma=2.5 head_offset=100 seed=1, symmetrised, deduplicated",
+                       "nnz": int(col.numel()), "mean_nodes_per_batch": round(mean_nodes, 1),
+                       "streams_in_flight": D, "scale": args.scale,
+                       "l2": "inputs larger than L2 (feature table + CSR >> 126 MB, random rows)"},
+            "gathered_GBps": round(value * mean_nodes * row_bytes / 1e9, 2),
+            "e2e": {"value": round(e2e_v, 2), "unit": UNIT, "h2d_bytes_per_step": bs * 8,
+                    "d2h_bytes_per_step": 8 * 32 + (8 * 18 if P > 1 else 0),
+                    "gathered_GBps": round(world * e2e_nodes * row_bytes / t_e2e / 1e9, 2),
+                    "api": "FastSampler -> " + ("DeviceDistributedPrefetcher" if P > 1 else "DevicePrefetcher")},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "k_gather (feature gather)", "achieved": round(achieved, 1),
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak_source": peak_src, "avg_launch_ms": round(g_ms_avg, 5),
+                         "algorithmic_bytes_per_launch": int(alg_bytes_per_launch),
+                         "bytes_model": "N_b * (2*row_bytes + 4)", "launches_timed": len(evs)},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (testing only)")
+    ap.add_argument("--depth", type=int, default=4, help="mini-batches in flight (CUDA streams)")
+    ap.add_argument("--cache-pct", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-e2e", action="store_true", help="cProfile the public-API loop (stderr)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

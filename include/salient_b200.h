@@ -143,15 +143,18 @@ typedef struct spp_graph {
 /* Per-stream scratch of the sampler (caller allocates; sizes from spp_sampler_sizes). */
 typedef struct spp_sampler_ws {
   uint64_t* table;       /* hash table, table_slots entries of {key+1, ~local}                 */
-  int64_t table_slots;   /* power of two, >= 2 * max_nodes                                     */
+  int64_t table_slots;   /* power of two, >= 1.25 * max_nodes (spp_sampler_sizes gives >= 1.5x) */
   int32_t* n_ids;        /* int32[max_nodes]   global ids in first-discovery order             */
   int64_t max_nodes;
   int64_t* tgt_start;    /* int64[max_targets] rowptr[n] of each frontier node                  */
   int32_t* tgt_deg;      /* int32[max_targets]                                                  */
   int64_t max_targets;   /* frontier bound of the last hop                                     */
-  uint64_t* tile_state;  /* uint64[tile_words] decoupled look-back state                        */
+  uint64_t* tile_state;  /* uint64[tile_words] scan state; MUST be zero when first used         */
   int64_t tile_words;
   int64_t* meta;         /* int64[SPP_META_WORDS]                                               */
+  int32_t* cand;         /* int32[cand_words] candidate slots of the fused sampled-hop path     */
+                         /* (NULL: always use the general path)                                  */
+  int64_t cand_words;
 } spp_sampler_ws;
 
 typedef struct spp_sampler_sizes_t {
@@ -159,6 +162,7 @@ typedef struct spp_sampler_sizes_t {
   int64_t max_targets;      /* bound on the last hop's frontier                                */
   int64_t table_slots;
   int64_t tile_words;
+  int64_t cand_words;
   int64_t hop_targets[SPP_MAX_HOPS]; /* bound T_h                                              */
   int64_t hop_edges[SPP_MAX_HOPS];   /* bound E_h (-1: data dependent, full neighbourhood)     */
 } spp_sampler_sizes_t;

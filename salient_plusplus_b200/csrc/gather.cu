@@ -9,6 +9,8 @@
 // store (L1::no_allocate on both sides: every byte is touched once).
 //
 // Algorithmic bytes per row: 2 * row_bytes + sizeof(index)   (DESIGN.md section 4).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace spp {
@@ -115,9 +117,19 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
   }
 }
 
+// Experiment hook: SPP_L2_FETCH_GRANULARITY=32|64|128 sets cudaLimitMaxL2FetchGranularity once.
+static void maybe_set_fetch_granularity() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = getenv("SPP_L2_FETCH_GRANULARITY");
+  if (e && *e) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+}
+
 template <bool kPartitioned>
 static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaStream_t st) {
   if (prm.n_max <= 0) return 0;
+  maybe_set_fetch_granularity();
   prm.vpr = (uint32_t)(prm.row_bytes / vec_bytes);
   if ((uint64_t)prm.vpr * kRows >= (1ull << 31))
     return fail(SPP_EUNSUPPORTED, "gather: row of %lld bytes too wide", (long long)prm.row_bytes);

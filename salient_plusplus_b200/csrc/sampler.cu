@@ -19,6 +19,8 @@
 //                         (std::sort at sample_cpu.hpp:126), int64 output.
 //
 // Hash entry: 64 bits = { key + 1 , ~local } ; empty = 0, so the table is cleared by a memset.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace spp {
@@ -556,6 +558,263 @@ __global__ void k_export_nids(const int32_t* __restrict__ n_ids, const int64_t* 
     out[i] = (OutT)n_ids[i];
 }
 
+// ================================================================================================
+// Fused path for sampled hops with 1 <= fanout <= 32 (every reference configuration):
+//   A. k_hop_sample_fused   reads rowptr itself (no separate degree pass), candidate (i, j) lives at
+//                           the fixed-stride virtual position v = i * k + j (ordering key T + v),
+//                           slot of each candidate -> cand[v] (kInvalidCand for j >= kept count);
+//                           optimistic CAS insert: one L2 round trip per candidate.
+//   B. k_hop_compact_fused  one pass over the virtual positions: kept-edge count and first-discoverer
+//                           count scanned together -> out_rowptr, n_ids, new local ids.  The scan is
+//                           "aggregate only": a tile publishes its own totals at once and sums the
+//                           totals of all earlier tiles in parallel, so there is no serial prefix
+//                           chain (the tile counts here are <= ~1000).
+//   C. k_relabel_sort_fused slot -> local id, register bitonic sort per row, compacted int64 row.
+// ================================================================================================
+constexpr uint32_t kInvalidCand = 0xFFFFFFFFu;
+constexpr int kFusedItems = 8;
+constexpr int kFusedTile = kScanThreads * kFusedItems;  // 2048 virtual positions per tile
+
+__device__ __forceinline__ uint32_t table_insert_optimistic(const Table& t, int32_t key) {
+  const uint32_t want = (uint32_t)key + 1u;
+  uint32_t slot = table_home(t, key);
+  while (true) {
+    const uint32_t prev = atomicCAS(t.w + 2 * (size_t)slot, 0u, want);
+    if (prev == 0u || prev == want) return slot;
+    slot = (slot + 1) & t.mask;
+  }
+}
+
+struct FusedParams {
+  HopParams h;
+  uint32_t* cand;    // uint32[T * k] slot of every virtual candidate
+  int64_t cand_cap;  // capacity of cand (elements)
+  uint32_t epoch;    // tag of this launch's tile aggregates
+};
+
+template <int G, bool kCol64>
+__global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __grid_constant__ FusedParams fp) {
+  const HopParams& prm = fp.h;
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) T = prm.max_targets;
+  const int k = prm.fanout;
+  if ((uint64_t)T * (uint64_t)k > (uint64_t)fp.cand_cap || (uint64_t)T * (uint64_t)(k + 1) >= 0xFFFFFFF0ull) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_OVERFLOW] = 1;
+    return;
+  }
+  const uint32_t Tbase = (uint32_t)T;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int gbase = lane & ~(G - 1);
+  constexpr int kGroupsPerWarp = 32 / G;
+  const int64_t warp_global = ((int64_t)blockIdx.x * kSampleThreads + threadIdx.x) >> 5;
+  const int64_t stride = (((int64_t)gridDim.x * kSampleThreads) >> 5) * kGroupsPerWarp;
+
+  // software pipeline: the (node, rowptr pair) of the next target is in flight while the current
+  // target's col reads and table atomics are outstanding
+  int64_t i = warp_global * kGroupsPerWarp + (lane / G);
+  int64_t nstart = 0, nend = 0;
+  if (i < T) {
+    const int32_t n = prm.n_ids[i];
+    nstart = __ldg(prm.rowptr + n);
+    nend = __ldg(prm.rowptr + n + 1);
+  }
+  for (int64_t i0 = warp_global * kGroupsPerWarp; i0 < T; i0 += stride) {
+    const bool valid = i < T;
+    const int64_t start = nstart;
+    const int32_t deg = (int32_t)(nend - nstart);
+    const int64_t icur = i;
+    i += stride;
+    if (i < T) {
+      const int32_t n = prm.n_ids[i];
+      nstart = __ldg(prm.rowptr + n);
+      nend = __ldg(prm.rowptr + n + 1);
+    }
+    const bool need = valid && deg > k;
+    const int32_t basej = deg - k;
+    uint32_t myr = 0, mypick = 0xffffffffu;
+    if (need && gl < k)
+      myr = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)icur, (uint32_t)gl), (uint32_t)(basej + gl) + 1u);
+    if (__any_sync(kFullMask, need)) {
+#pragma unroll 1
+      for (int s = 0; s < k; ++s) {  // Floyd: t uniform on [0, basej+s]; taken already -> basej+s
+        const uint32_t t = __shfl_sync(kFullMask, myr, gbase + s);
+        const uint32_t b = __ballot_sync(kFullMask, need && gl < s && mypick == t);
+        const uint32_t gm = (G == 32) ? b : ((b >> gbase) & ((1u << G) - 1u));
+        if (gl == s) mypick = gm ? (uint32_t)(basej + s) : t;
+      }
+    }
+    const int32_t c = deg < k ? deg : k;
+    if (valid && gl < k) {
+      const int64_t v = icur * k + gl;
+      uint32_t slot = kInvalidCand;
+      if (gl < c) {
+        const uint32_t pick = need ? mypick : (uint32_t)gl;
+        const int32_t node = load_col<kCol64>(prm.col, start + pick);
+        slot = table_insert_optimistic(prm.tab, node);
+        atomicMax(prm.tab.w + 2 * (size_t)slot + 1, ~(Tbase + (uint32_t)v));
+      }
+      fp.cand[v] = slot;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid_constant__ FusedParams fp) {
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  __shared__ unsigned long long s_red[kScanThreads / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ int64_t s_tile;
+  const HopParams& prm = fp.h;
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) T = prm.max_targets;
+  const int k = prm.fanout;
+  int64_t V = T * k;
+  if (V > fp.cand_cap || (uint64_t)T * (uint64_t)(k + 1) >= 0xFFFFFFF0ull) V = 0;  // overflow flagged by the sampler
+  const uint32_t Tbase = (uint32_t)T;
+  const int64_t num_tiles = (V + kFusedTile - 1) / kFusedTile;
+  unsigned long long* ctr = (unsigned long long*)prm.tile_state;        // [0] dynamic tile counter
+  unsigned long long* done = ctr + 1;                                   // [1] CTAs finished
+  uint64_t* agg = prm.tile_state + 2;                                   // [2 + t] epoch | kept | new
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    prm.out_rowptr[0] = 0;
+    if (V == 0) {
+      prm.meta[SPP_META_EDGES(prm.hop)] = 0;
+      prm.meta[SPP_META_NODES(prm.hop + 1)] = T;
+    }
+  }
+  // rows without a virtual position (V == 0 because of an overflow) are left untouched
+  while (true) {
+    if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ctr, 1ull);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    if (tile >= num_tiles) break;
+    const int64_t v0 = tile * kFusedTile + (int64_t)threadIdx.x * kFusedItems;
+    uint32_t slot[kFusedItems];
+    uint32_t keptm = 0, newm = 0;
+#pragma unroll
+    for (int q = 0; q < kFusedItems; ++q) slot[q] = (v0 + q < V) ? fp.cand[v0 + q] : kInvalidCand;
+#pragma unroll
+    for (int q = 0; q < kFusedItems; ++q) {
+      if (slot[q] != kInvalidCand) {
+        keptm |= 1u << q;
+        const uint32_t enc = __ldcg(prm.tab.w + 2 * (size_t)slot[q] + 1);
+        if (enc == ~(Tbase + (uint32_t)(v0 + q))) newm |= 1u << q;
+      }
+    }
+    // packed (kept << 16 | new) block scan: per-tile sums are <= 2048 each
+    const uint32_t mine = ((uint32_t)__popc(keptm) << 16) | (uint32_t)__popc(newm);
+    uint32_t inc = warp_incl_scan(mine, lane);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+      const uint32_t x = s_warp[w];
+      if (w < warp) wbase += x;
+      total += x;
+    }
+    const uint32_t texcl = wbase + inc - mine;
+    if (threadIdx.x == 0) st_volatile_u64(agg + tile, ((uint64_t)fp.epoch << 32) | (uint64_t)total);
+    // sum of the aggregates of every earlier tile (published independently of their own waits)
+    unsigned long long acc = 0;  // kept in the high 32 bits, new in the low 32 bits
+    for (int64_t t = threadIdx.x; t < tile; t += kScanThreads) {
+      uint64_t w;
+      do {
+        w = ld_volatile_u64(agg + t);
+      } while ((uint32_t)(w >> 32) != fp.epoch);
+      acc += ((unsigned long long)((uint32_t)w >> 16) << 32) | (unsigned long long)((uint32_t)w & 0xffffu);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long b = 0;
+#pragma unroll
+      for (int w = 0; w < kScanThreads / 32; ++w) b += s_red[w];
+      s_base = b;
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+    uint64_t kept_run = (base >> 32) + (texcl >> 16);
+    uint64_t new_run = (base & 0xffffffffull) + (texcl & 0xffffu);
+    // row bookkeeping: v = i * k + r
+    int64_t row = v0 / k;
+    int r = (int)(v0 - row * k);
+#pragma unroll
+    for (int q = 0; q < kFusedItems; ++q) {
+      if (v0 + q < V) {
+        if (keptm & (1u << q)) ++kept_run;
+        if (newm & (1u << q)) {
+          const int64_t L = T + (int64_t)new_run;
+          if (L < prm.max_nodes) {
+            uint32_t* ent = prm.tab.w + 2 * (size_t)slot[q];
+            prm.n_ids[L] = (int32_t)(__ldcg(ent) - 1u);
+            __stcg(ent + 1, ~(uint32_t)L);
+          }
+          ++new_run;
+        }
+        if (r == k - 1) prm.out_rowptr[row + 1] = (int64_t)kept_run;
+        if (++r == k) {
+          r = 0;
+          ++row;
+        }
+      }
+    }
+    if (tile == num_tiles - 1 && threadIdx.x == 0) {
+      const uint64_t kept_total = (base >> 32) + (total >> 16);
+      int64_t S = T + (int64_t)((base & 0xffffffffull) + (total & 0xffffu));
+      if (S > prm.max_nodes) {
+        prm.meta[SPP_META_OVERFLOW] = 1;
+        S = prm.max_nodes;
+      }
+      if ((int64_t)kept_total > prm.max_edges) prm.meta[SPP_META_OVERFLOW] = 1;  // out_col too small
+      prm.meta[SPP_META_EDGES(prm.hop)] = (int64_t)kept_total;
+      prm.meta[SPP_META_NODES(prm.hop + 1)] = S;
+    }
+    __syncthreads();  // s_tile / s_base reuse
+  }
+  // the last CTA out re-arms the counters for the next launch on this workspace
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      *ctr = 0ull;
+      *done = 0ull;
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kSampleThreads) k_relabel_sort_fused(const __grid_constant__ FusedParams fp) {
+  const HopParams& prm = fp.h;
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) T = prm.max_targets;
+  if (prm.meta[SPP_META_OVERFLOW]) return;
+  const int k = prm.fanout;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  constexpr int kGroupsPerWarp = 32 / G;
+  const int64_t warp_global = ((int64_t)blockIdx.x * kSampleThreads + threadIdx.x) >> 5;
+  const int64_t warps_total = ((int64_t)gridDim.x * kSampleThreads) >> 5;
+  for (int64_t i0 = warp_global * kGroupsPerWarp; i0 < T; i0 += warps_total * kGroupsPerWarp) {
+    const int64_t i = i0 + (lane / G);
+    int64_t p0 = 0;
+    int n = 0;
+    if (i < T) {
+      p0 = prm.out_rowptr[i];
+      n = (int)(prm.out_rowptr[i + 1] - p0);
+    }
+    int32_t v = 0x7fffffff;
+    if (gl < n) {
+      const uint32_t slot = fp.cand[i * k + gl];
+      v = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
+    }
+    v = group_bitonic_sort<G>(v, gl);
+    if (gl < n) prm.out_col[p0 + gl] = (int64_t)v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -565,8 +824,8 @@ static int check_ws(const spp_sampler_ws* ws) {
     return fail(SPP_EINVAL, "sampler: workspace has null members");
   if (ws->table_slots < 2 || (ws->table_slots & (ws->table_slots - 1)) || ws->table_slots > (1ll << 31))
     return fail(SPP_EINVAL, "sampler: table_slots must be a power of two in [2, 2^31]");
-  if (ws->table_slots < 2 * ws->max_nodes)
-    return fail(SPP_ECAPACITY, "sampler: table_slots (%lld) < 2 * max_nodes (%lld)", (long long)ws->table_slots,
+  if (ws->table_slots * 4 < 5 * ws->max_nodes)
+    return fail(SPP_ECAPACITY, "sampler: table_slots (%lld) < 1.25 * max_nodes (%lld)", (long long)ws->table_slots,
                 (long long)ws->max_nodes);
   return 0;
 }
@@ -611,12 +870,16 @@ static int scan_grid(int64_t bound_items) {
   return (int)(tiles < cap ? tiles : cap);
 }
 
+// The general (look-back) path owns tile_state[2..] and clears what it uses before every scan;
+// words [0] and [1] belong to the fused path (self-resetting tile counter / finished-CTA count).
+constexpr int kGeneralTileOffset = 2;
+
 static int reset_tiles(const spp_sampler_ws* ws, int64_t bound_items, cudaStream_t st) {
   int64_t words = 1 + ceil_div(bound_items > 0 ? bound_items : 1, kScanTile);
-  if (words > ws->tile_words)
-    return fail(SPP_ECAPACITY, "sampler: tile_state too small (%lld words needed, %lld given)", (long long)words,
-                (long long)ws->tile_words);
-  SPP_CUDA(cudaMemsetAsync(ws->tile_state, 0, (size_t)words * sizeof(uint64_t), st));
+  if (words + kGeneralTileOffset > ws->tile_words)
+    return fail(SPP_ECAPACITY, "sampler: tile_state too small (%lld words needed, %lld given)",
+                (long long)(words + kGeneralTileOffset), (long long)ws->tile_words);
+  SPP_CUDA(cudaMemsetAsync(ws->tile_state + kGeneralTileOffset, 0, (size_t)words * sizeof(uint64_t), st));
   return 0;
 }
 
@@ -639,6 +902,7 @@ static int launch_count(const spp_graph* g, int hop, int32_t fanout, int replace
   if (!out_rowptr) return fail(SPP_EINVAL, "sampler: null out_rowptr");
   if (int r = reset_tiles(ws, max_targets, st)) return r;
   HopParams p = make_params(g, ws, hop, fanout, replace, 0, max_targets, 0, out_rowptr, nullptr);
+  p.tile_state += kGeneralTileOffset;
   k_hop_count_scan<<<scan_grid(p.max_targets), kScanThreads, 0, st>>>(p);
   SPP_KERNEL_CHECK("k_hop_count_scan");
   return 0;
@@ -659,6 +923,7 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
     return fail(SPP_EUNSUPPORTED, "sampler: fanout %d > SPP_MAX_FANOUT (%d)", fanout, SPP_MAX_FANOUT);
   HopParams p = make_params(g, ws, hop, fanout, replace, rng_seed, max_targets, max_edges,
                             const_cast<int64_t*>(out_rowptr), out_col);
+  p.tile_state += kGeneralTileOffset;
   const bool c64 = g->col_is_64 != 0;
   const int sms = num_sms();
   // groups needed ~ targets; persistent grid, 8 CTAs / SM at most
@@ -718,6 +983,65 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
   return 0;
 }
 
+static std::atomic<uint32_t> g_epoch{1};
+
+static bool fused_ok(int32_t fanout, int replace, const spp_sampler_ws* ws) {
+  return fanout >= 1 && fanout <= 32 && !replace && ws->cand != nullptr;
+}
+
+// one sampled hop through the fused path (no host synchronisation, no memset)
+static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_t rng_seed, int64_t max_targets,
+                            int64_t max_edges, const spp_sampler_ws* ws, int64_t* out_rowptr, int64_t* out_col,
+                            cudaStream_t st) {
+  if (hop < 0 || hop >= SPP_MAX_HOPS) return fail(SPP_EINVAL, "sampler: hop %d out of range", hop);
+  if (!out_rowptr || (!out_col && max_edges > 0)) return fail(SPP_EINVAL, "sampler: null output");
+  FusedParams fp{};
+  fp.h = make_params(g, ws, hop, fanout, 0, rng_seed, max_targets, max_edges, out_rowptr, out_col);
+  const int64_t vmax = fp.h.max_targets * (int64_t)fanout;
+  if (vmax > ws->cand_words)
+    return fail(SPP_ECAPACITY, "sampler: cand buffer too small (%lld needed, %lld given)", (long long)vmax,
+                (long long)ws->cand_words);
+  const int64_t tiles = ceil_div(vmax > 0 ? vmax : 1, kFusedTile);
+  if (2 + tiles > ws->tile_words)
+    return fail(SPP_ECAPACITY, "sampler: tile_state too small (%lld words needed)", (long long)(2 + tiles));
+  fp.cand = reinterpret_cast<uint32_t*>(ws->cand);
+  fp.cand_cap = ws->cand_words;
+  // epochs stay in [1, 2^30): they can never equal the high word of a look-back state
+  // (status << 30) left behind in the shared aggregate area by the general path
+  fp.epoch = (g_epoch.fetch_add(1, std::memory_order_relaxed) % 0x3FFFFFFFu) + 1u;
+  const bool c64 = g->col_is_64 != 0;
+  const int sms = num_sms();
+  const int G = fanout <= 4 ? 4 : fanout <= 8 ? 8 : fanout <= 16 ? 16 : 32;
+  int64_t warps = ceil_div(fp.h.max_targets > 0 ? fp.h.max_targets : 1, 32 / G);
+  int64_t ctas = ceil_div(warps, kSampleThreads / 32);
+  int64_t cap = (int64_t)sms * 8;
+  const int grid = (int)(ctas < cap ? ctas : cap);
+#define SPP_FUSED_SAMPLE(GG)                                                                   \
+  do {                                                                                          \
+    if (c64) k_hop_sample_fused<GG, true><<<grid, kSampleThreads, 0, st>>>(fp);                 \
+    else k_hop_sample_fused<GG, false><<<grid, kSampleThreads, 0, st>>>(fp);                    \
+  } while (0)
+  switch (G) {
+    case 4: SPP_FUSED_SAMPLE(4); break;
+    case 8: SPP_FUSED_SAMPLE(8); break;
+    case 16: SPP_FUSED_SAMPLE(16); break;
+    default: SPP_FUSED_SAMPLE(32); break;
+  }
+#undef SPP_FUSED_SAMPLE
+  SPP_KERNEL_CHECK("k_hop_sample_fused");
+  const int64_t scap = (int64_t)sms * 6;
+  k_hop_compact_fused<<<(int)(tiles < scap ? tiles : scap), kScanThreads, 0, st>>>(fp);
+  SPP_KERNEL_CHECK("k_hop_compact_fused");
+  switch (G) {
+    case 4: k_relabel_sort_fused<4><<<grid, kSampleThreads, 0, st>>>(fp); break;
+    case 8: k_relabel_sort_fused<8><<<grid, kSampleThreads, 0, st>>>(fp); break;
+    case 16: k_relabel_sort_fused<16><<<grid, kSampleThreads, 0, st>>>(fp); break;
+    default: k_relabel_sort_fused<32><<<grid, kSampleThreads, 0, st>>>(fp); break;
+  }
+  SPP_KERNEL_CHECK("k_relabel_sort_fused");
+  return 0;
+}
+
 static int launch_export(const spp_sampler_ws* ws, int word, void* out, int out_is_64, int64_t max_nodes,
                          cudaStream_t st) {
   if (!out || max_nodes <= 0) return 0;
@@ -765,11 +1089,15 @@ int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes, int n_hops, int6
   out->max_nodes = T > 0 ? T : 1;
   out->max_targets = maxT > 0 ? maxT : 1;
   int64_t slots = 1024;
-  while (slots < 2 * out->max_nodes) slots <<= 1;
+  while (2 * slots < 3 * out->max_nodes) slots <<= 1;  // load factor <= 2/3 at the node bound
   if (slots > (1ll << 31)) return fail(SPP_EUNSUPPORTED, "spp_sampler_sizes: node bound %lld too large", (long long)T);
   out->table_slots = slots;
   int64_t items = maxE > maxT ? maxE : maxT;
   out->tile_words = 2 + ceil_div(items > 0 ? items : 1, kScanTile) + 30;
+  int64_t cw = 0;  // fused path: virtual candidates of a sampled hop
+  for (int h = 0; h < n_hops; ++h)
+    if (sizes[h] >= 1 && sizes[h] <= 32 && out->hop_targets[h] * (int64_t)sizes[h] > cw) cw = out->hop_targets[h] * (int64_t)sizes[h];
+  out->cand_words = cw + 16;
   return 0;
 }
 
@@ -813,9 +1141,14 @@ int spp_sample_minibatch(const spp_graph* g, const int64_t* seeds, int64_t batch
   int64_t T = batch_size;
   for (int h = 0; h < n_hops; ++h) {
     int64_t Tb = T < ws->max_targets ? T : ws->max_targets;
-    if (int r = launch_count(g, h, sizes[h], replace, Tb, ws, out_rowptr[h], st)) return r;
-    if (int r = launch_fill(g, h, sizes[h], replace, rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st))
-      return r;
+    if (fused_ok(sizes[h], replace, ws)) {
+      if (int r = launch_hop_fused(g, h, sizes[h], rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st))
+        return r;
+    } else {
+      if (int r = launch_count(g, h, sizes[h], replace, Tb, ws, out_rowptr[h], st)) return r;
+      if (int r = launch_fill(g, h, sizes[h], replace, rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st))
+        return r;
+    }
     int64_t next = T + out_col_cap[h];
     T = next < ws->max_nodes ? next : ws->max_nodes;
   }

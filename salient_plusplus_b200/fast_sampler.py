@@ -138,19 +138,21 @@ class _Workspace:
         self.n_ids = torch.empty(self.max_nodes, dtype=torch.int32, device=device)
         self.tgt_start = torch.empty(self.max_targets, dtype=torch.int64, device=device)
         self.tgt_deg = torch.empty(self.max_targets, dtype=torch.int32, device=device)
-        self.tile_state = torch.empty(int(sz.tile_words), dtype=torch.int64, device=device)
+        self.tile_state = torch.zeros(int(sz.tile_words), dtype=torch.int64, device=device)
         self.meta = torch.zeros(SPP_META_WORDS, dtype=torch.int64, device=device)
+        self.cand = torch.empty(int(sz.cand_words), dtype=torch.int32, device=device)
         self._refresh()
 
     def _refresh(self):
         self.c = SamplerWs(self.table.data_ptr(), self.table.numel(), self.n_ids.data_ptr(), self.max_nodes,
                            self.tgt_start.data_ptr(), self.tgt_deg.data_ptr(), self.max_targets,
-                           self.tile_state.data_ptr(), self.tile_state.numel(), self.meta.data_ptr())
+                           self.tile_state.data_ptr(), self.tile_state.numel(), self.meta.data_ptr(),
+                           self.cand.data_ptr(), self.cand.numel())
 
     def ensure_tiles(self, items: int):
         words = 2 + (max(items, 1) + 1023) // 1024 + 30
         if words > self.tile_state.numel():
-            self.tile_state = torch.empty(words, dtype=torch.int64, device=self.table.device)
+            self.tile_state = torch.zeros(words, dtype=torch.int64, device=self.table.device)
             self._refresh()
 
     def meta_ptr(self, word: int) -> int:
@@ -527,12 +529,39 @@ def _batch_ranges(n: int, cfg: Config) -> List[Tuple[int, int]]:
 
 
 class _Slot:
-    def __init__(self, ws: _Workspace, device, extra_words: int):
-        self.ws = ws
+    """One in-flight mini-batch: sampler workspace, CUDA stream, completion event, pinned meta
+    block.  Slots are recycled across Sessions (a new Session is created every epoch,
+    fast_trainer/samplers.py:394-396) through ``_SLOT_POOL`` so that epoch start-up does not
+    re-allocate hash tables and streams."""
+
+    def __init__(self, sz: SamplerSizes, device, max_bs: int, split_words: int):
+        self.ws = _Workspace(sz, device)
         self.stream = torch.cuda.Stream(device)
         self.event = torch.cuda.Event()
-        self.meta_host = torch.empty(SPP_META_WORDS + extra_words, dtype=torch.int64).pin_memory()
+        self.meta_host = torch.empty(SPP_META_WORDS + SPP_MAX_PARTS + 2, dtype=torch.int64).pin_memory()
+        self.seeds = torch.empty(max(max_bs, 1), dtype=torch.int64, device=device)
+        if split_words:
+            self.split_scratch = torch.empty(split_words, dtype=torch.int32, device=device)
+            self.counts = torch.zeros(SPP_MAX_PARTS + 2, dtype=torch.int64, device=device)
         self.job = None
+        self.c_rp = (c_vp * SPP_MAX_HOPS)()
+        self.c_cp = (c_vp * SPP_MAX_HOPS)()
+
+
+_SLOT_POOL: dict = {}
+_EMPTY_EID: dict = {}
+
+
+def _empty_eid(device) -> torch.Tensor:
+    """e_id is always empty (fast_sampler/sample_cpu.hpp:120); one shared tensor per device."""
+    t = _EMPTY_EID.get(device)
+    if t is None:
+        t = _EMPTY_EID[device] = torch.empty(0, dtype=torch.int64, device=device)
+    return t
+
+
+def clear_slot_pool() -> None:
+    _SLOT_POOL.clear()
 
 
 class Session:
@@ -549,8 +578,14 @@ class Session:
         if len(self._sizes) > SPP_MAX_HOPS:
             raise RuntimeError(f"at most {SPP_MAX_HOPS} hops are supported")
         self._g = _DeviceGraph.get(cfg.rowptr, cfg.col)
-        self._idx = cfg.idx.to(device=self._device, dtype=torch.int64).contiguous()
-        self._ranges = _batch_ranges(self._idx.numel(), cfg)
+        # Seeds: a device-resident idx is used in place; a host idx (what the reference's driver
+        # passes) is pinned once and each batch's slice is copied H2D on that batch's stream.
+        idx = cfg.idx.to(torch.int64).contiguous()
+        if idx.is_cuda:
+            self._idx, self._idx_host = idx, None
+        else:
+            self._idx, self._idx_host = None, (idx.pin_memory() if idx.numel() else idx)
+        self._ranges = _batch_ranges(idx.numel(), cfg)
         self._num_total = len(self._ranges)
         self._num_consumed = 0
         self._next = 0
@@ -561,18 +596,32 @@ class Session:
         if self._y is not None and self._y.dim() == 1:
             self._y = self._y.view(-1, 1)
         self._setup_features()
+        self._row_bytes = self._feat_shape[0] * torch.empty(0, dtype=self._feat_shape[1]).element_size()
         max_bs = max((e - s for s, e in self._ranges), default=0)
         self._sz = _sampler_sizes(max_bs, self._sizes, self._g)
         depth = int(os.environ.get("SPP_SESSION_DEPTH", "4"))
         depth = max(1, min(depth, int(max_items_in_queue), max(self._num_total, 1)))
-        P = self._P if cfg.distributed else 0
-        self._slots = [_Slot(_Workspace(self._sz, self._device), self._device, SPP_MAX_PARTS + 2)
-                       for _ in range(depth)]
+        split_words = int(self._lib.spp_split_scratch_words(self._sz.max_nodes)) if cfg.distributed else 0
+        sz = self._sz
+        self._pool_key = (self._device.index, int(sz.max_nodes), int(sz.max_targets), int(sz.table_slots),
+                          int(sz.tile_words), int(sz.cand_words), max_bs, split_words)
+        pool = _SLOT_POOL.setdefault(self._pool_key, [])
+        self._slots = [pool.pop() if pool else _Slot(sz, self._device, max_bs, split_words) for _ in range(depth)]
+        self._released = False
+        # arena layout (int64 words) of one batch's structure outputs, at their upper bounds
+        L = len(self._sizes)
+        self._arena_off = []
+        o = 0
+        for h in range(L):
+            T, E = int(sz.hop_targets[h]), max(int(sz.hop_edges[h]), 1)
+            self._arena_off.append((o, o + T + 1))
+            o += T + 1 + E
+        self._arena_nid = o
         if cfg.distributed:
-            words = int(self._lib.spp_split_scratch_words(self._sz.max_nodes))
-            for s in self._slots:
-                s.split_scratch = torch.empty(words, dtype=torch.int32, device=self._device)
-                s.counts = torch.zeros(SPP_MAX_PARTS + 2, dtype=torch.int64, device=self._device)
+            o += 3 * int(sz.max_nodes)  # n_id, bucket_ids, perm
+        self._arena_words = max(o, 1)
+        self._c_sizes = (ctypes.c_int32 * max(L, 1))(*self._sizes)
+        self._c_caps = (ctypes.c_int64 * max(L, 1))(*[int(sz.hop_edges[h]) for h in range(L)])
         self._free = deque(self._slots)
         self._pending: deque = deque()
         self._freq = None
@@ -670,24 +719,40 @@ class Session:
         bs = stop - start
         cfg = self._config
         rng_seed = (stop * 17 + 5) & 0xFFFFFFFF  # fast_sampler.cpp:994
-        seeds_ptr = self._idx.data_ptr() + 8 * start
         L = len(self._sizes)
         job = {"range": (start, stop), "bs": bs}
         with torch.cuda.stream(slot.stream):
             sp = slot.stream.cuda_stream
             ws = slot.ws
+            if self._idx_host is not None:
+                seeds = slot.seeds[:bs]
+                if bs:
+                    seeds.copy_(self._idx_host[start:stop], non_blocking=True)
+            else:
+                seeds = self._idx[start:stop]
+            seeds_ptr = seeds.data_ptr()
+            arena = None
             if self._full:
-                nb, adjs = _sample_stepwise(self._g, ws, self._idx[start:stop], self._sizes, False, rng_seed,
+                nb, adjs = _sample_stepwise(self._g, ws, seeds, self._sizes, False, rng_seed,
                                             self._device)
                 job["ready"] = (nb, adjs)
             else:
-                job["rowptrs"], job["cols"], n_id = _sample_fused(
-                    self._g, ws, self._sz, seeds_ptr, bs, self._sizes, False, rng_seed, sp, self._device,
-                    cfg.distributed)
-                job["n_id"] = n_id
+                # one allocation for every structure output of the batch (rowptr / col per hop,
+                # and n_id / bucket ids / perm in distributed mode); exact-size views are cut in
+                # _finalize once the meta block has arrived
+                arena = torch.empty(self._arena_words, dtype=torch.int64, device=self._device)
+                base = arena.data_ptr()
+                for h, (ro, co) in enumerate(self._arena_off):
+                    slot.c_rp[h] = base + 8 * ro
+                    slot.c_cp[h] = base + 8 * co
+                nid_ptr = base + 8 * self._arena_nid if cfg.distributed else None
+                check(self._lib.spp_sample_minibatch(ctypes.byref(self._g.c), seeds_ptr, bs, self._c_sizes, L, 0,
+                                                     ctypes.c_uint64(rng_seed), ctypes.byref(ws.c), slot.c_rp,
+                                                     slot.c_cp, self._c_caps, nid_ptr, sp), "spp_sample_minibatch")
+                job["arena"] = arena
             n_dev = ws.meta_ptr(L)
             fdim, fdtype = self._feat_shape
-            row_bytes = fdim * torch.empty(0, dtype=fdtype).element_size()
+            row_bytes = self._row_bytes
             if not cfg.distributed:
                 if self._x_table is not None:
                     x = torch.empty((ws.max_nodes, fdim), dtype=fdtype, device=self._device)
@@ -699,12 +764,17 @@ class Session:
                 job["x"] = x
             else:
                 if self._full:
-                    n_id = torch.empty(ws.max_nodes, dtype=torch.int64, device=self._device)
+                    arena = torch.empty(3 * ws.max_nodes, dtype=torch.int64, device=self._device)
+                    n_id = arena[:ws.max_nodes]
                     check(self._lib.spp_sample_export_nids(ctypes.byref(ws.c), L, n_id.data_ptr(), 1, ws.max_nodes, sp),
                           "spp_sample_export_nids")
-                    job["n_id"] = n_id
-                bucket_ids = torch.empty(ws.max_nodes, dtype=torch.int64, device=self._device)
-                perm = torch.empty(ws.max_nodes, dtype=torch.int64, device=self._device)
+                    o = 0
+                else:
+                    o = self._arena_nid
+                    n_id = arena[o:o + ws.max_nodes]
+                job["n_id"] = n_id
+                bucket_ids = arena[o + ws.max_nodes:o + 2 * ws.max_nodes]
+                perm = arena[o + 2 * ws.max_nodes:o + 3 * ws.max_nodes]
                 check(self._lib.spp_split_by_owner(ctypes.byref(self._split_fm), int(self._use_cache),
                                                    ws.n_ids.data_ptr(), 0, ws.max_nodes, n_dev, bucket_ids.data_ptr(),
                                                    perm.data_ptr(), slot.counts.data_ptr(),
@@ -738,7 +808,16 @@ class Session:
         if "ready" in job:
             nb, adjs = job["ready"]
         else:
-            nb, adjs = _finish_fused(slot.meta_host[:SPP_META_WORDS], job["rowptrs"], job["cols"], L)
+            m = slot.meta_host.tolist()
+            if m[META_OVERFLOW]:
+                raise SalientB200Error("sampler buffer bound exceeded on the device (SPP_META_OVERFLOW)")
+            arena, e_id = job["arena"], _empty_eid(self._device)
+            adjs = []
+            for h in range(L - 1, -1, -1):  # reversed like fast_sampler.cpp:224
+                ro, co = self._arena_off[h]
+                T, E = m[h], m[META_EDGES0 + h]
+                adjs.append((arena[ro:ro + T + 1], arena[co:co + E], e_id, (T, m[h + 1])))
+            nb = m[L]
         start, stop = job["range"]
         if not cfg.distributed:
             x = job["x"]
@@ -775,7 +854,27 @@ class Session:
         self._free.append(slot)
         while self._free and self._next < self._num_total:
             self._enqueue()
+        if self._num_consumed == self._num_total:
+            self._release_slots()
         return out
+
+    def _release_slots(self):
+        if self._released:
+            return
+        self._released = True
+        for s in self._pending:  # abandoned in-flight work (Session dropped early)
+            s.stream.synchronize()
+            s.job = None
+        self._pending.clear()
+        _SLOT_POOL.setdefault(self._pool_key, []).extend(self._slots)
+        self._slots = []
+        self._free = deque()
+
+    def __del__(self):
+        try:
+            self._release_slots()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def _count_remote(self, b: ProtoDistributedBatch):
         # fast_sampler.cpp:1093-1103 (set-up-time statistics for cache_strategy=simulation)

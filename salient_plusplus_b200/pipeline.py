@@ -1,0 +1,121 @@
+"""Device-resident mini-batch pipeline: the same C-ABI launch sequence the Session issues
+(sampler -> [owner split] -> feature gather -> label gather), but with static per-slot output
+buffers and no host synchronisation between batches.  bench.py uses it for the kernel-only
+throughput (`value`) and the per-kernel roofline pass; the Session (fast_sampler.py) is the
+public, reference-shaped API on top of the same calls."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import SPP_META_WORDS, SPP_MAX_PARTS, FeatureMap, check
+from .fast_sampler import _DeviceGraph, _Workspace, _sampler_sizes
+
+c_vp = ctypes.c_void_p
+
+
+class _PipeSlot:
+    pass
+
+
+class MiniBatchPipeline:
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, sizes: Sequence[int], batch_size: int,
+                 x_table: Optional[torch.Tensor] = None, y_table: Optional[torch.Tensor] = None,
+                 feature_map: Optional[FeatureMap] = None, feat_dim: int = 0, feat_dtype=torch.float16,
+                 split: bool = False, use_cache: bool = False, depth: int = 4, device=None):
+        assert all(int(s) >= 0 for s in sizes), "the static pipeline covers sampled hops only"
+        self.lib = _lib.load()
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.g = _DeviceGraph.get(rowptr, col)
+        self.sizes = [int(s) for s in sizes]
+        self.L = len(self.sizes)
+        self.bs = int(batch_size)
+        self.sz = _sampler_sizes(self.bs, self.sizes, self.g)
+        self.x_table, self.y_table, self.fm = x_table, y_table, feature_map
+        if x_table is not None:
+            feat_dim, feat_dtype = x_table.size(1), x_table.dtype
+        self.feat_dim, self.feat_dtype = feat_dim, feat_dtype
+        self.row_bytes = feat_dim * torch.empty(0, dtype=feat_dtype).element_size()
+        self.split, self.use_cache = split, use_cache
+        self.sz_arr = (ctypes.c_int32 * max(self.L, 1))(*self.sizes)
+        self.caps = (ctypes.c_int64 * max(self.L, 1))(*[int(self.sz.hop_edges[h]) for h in range(self.L)])
+        self.slots: List[_PipeSlot] = []
+        for _ in range(depth):
+            s = _PipeSlot()
+            s.ws = _Workspace(self.sz, self.device)
+            s.stream = torch.cuda.Stream(self.device)
+            s.rowptrs = [torch.empty(int(self.sz.hop_targets[h]) + 1, dtype=torch.int64, device=self.device)
+                         for h in range(self.L)]
+            s.cols = [torch.empty(max(int(self.sz.hop_edges[h]), 1), dtype=torch.int64, device=self.device)
+                      for h in range(self.L)]
+            s.rp = (c_vp * max(self.L, 1))(*[t.data_ptr() for t in s.rowptrs])
+            s.cp = (c_vp * max(self.L, 1))(*[t.data_ptr() for t in s.cols])
+            s.x = (torch.empty((s.ws.max_nodes, feat_dim), dtype=feat_dtype, device=self.device)
+                   if (x_table is not None or feature_map is not None) else None)
+            s.y = (torch.empty((self.bs, y_table.size(-1)), dtype=y_table.dtype, device=self.device)
+                   if y_table is not None else None)
+            if split:
+                words = int(self.lib.spp_split_scratch_words(s.ws.max_nodes))
+                s.scratch = torch.empty(words, dtype=torch.int32, device=self.device)
+                s.bucket_ids = torch.empty(s.ws.max_nodes, dtype=torch.int64, device=self.device)
+                s.perm = torch.empty(s.ws.max_nodes, dtype=torch.int64, device=self.device)
+                s.counts = torch.zeros(SPP_MAX_PARTS + 2, dtype=torch.int64, device=self.device)
+            s.meta_host = torch.empty(SPP_META_WORDS, dtype=torch.int64).pin_memory()
+            self.slots.append(s)
+        self.gather_events = None
+
+    # -- individual stages (all asynchronous on the slot's stream) ------------------------------
+    def sample(self, s: _PipeSlot, seeds_ptr: int, bs: int, rng_seed: int):
+        check(self.lib.spp_sample_minibatch(ctypes.byref(self.g.c), seeds_ptr, bs, self.sz_arr, self.L, 0,
+                                            ctypes.c_uint64(rng_seed), ctypes.byref(s.ws.c), s.rp, s.cp, self.caps,
+                                            None, s.stream.cuda_stream), "spp_sample_minibatch")
+
+    def gather(self, s: _PipeSlot):
+        n_dev = s.ws.meta_ptr(self.L)
+        if self.fm is not None:
+            check(self.lib.spp_gather_partitioned(ctypes.byref(self.fm), self.row_bytes, s.ws.n_ids.data_ptr(), 0,
+                                                  s.ws.max_nodes, n_dev, s.x.data_ptr(), s.ws.max_nodes, None,
+                                                  s.stream.cuda_stream), "spp_gather_partitioned")
+        elif self.x_table is not None:
+            check(self.lib.spp_gather_rows(self.x_table.data_ptr(), self.row_bytes, s.ws.n_ids.data_ptr(), 0,
+                                           s.ws.max_nodes, n_dev, s.x.data_ptr(), s.ws.max_nodes,
+                                           s.stream.cuda_stream), "spp_gather_rows")
+
+    def labels(self, s: _PipeSlot, seeds_ptr: int, bs: int):
+        if self.y_table is not None and bs > 0:
+            yb = self.y_table.size(-1) * self.y_table.element_size()
+            check(self.lib.spp_gather_rows(self.y_table.data_ptr(), yb, seeds_ptr, 1, bs, None, s.y.data_ptr(), bs,
+                                           s.stream.cuda_stream), "spp_gather_rows(y)")
+
+    def owner_split(self, s: _PipeSlot):
+        if self.split:
+            check(self.lib.spp_split_by_owner(ctypes.byref(self.fm), int(self.use_cache), s.ws.n_ids.data_ptr(), 0,
+                                              s.ws.max_nodes, s.ws.meta_ptr(self.L), s.bucket_ids.data_ptr(),
+                                              s.perm.data_ptr(), s.counts.data_ptr(), s.scratch.data_ptr(),
+                                              s.stream.cuda_stream), "spp_split_by_owner")
+
+    def launch(self, slot: int, seeds_ptr: int, bs: int, rng_seed: int, time_gather: bool = False):
+        """One mini-batch on slot ``slot``; returns the (start, end) events around the feature
+        gather when ``time_gather``."""
+        s = self.slots[slot]
+        self.sample(s, seeds_ptr, bs, rng_seed)
+        self.owner_split(s)
+        ev = None
+        if time_gather:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(s.stream)
+        self.gather(s)
+        if time_gather:
+            ev[1].record(s.stream)
+        self.labels(s, seeds_ptr, bs)
+        return ev
+
+    def read_meta(self, slot: int) -> List[int]:
+        s = self.slots[slot]
+        with torch.cuda.stream(s.stream):
+            s.meta_host.copy_(s.ws.meta, non_blocking=True)
+        s.stream.synchronize()
+        return s.meta_host.tolist()
