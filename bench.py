@@ -284,11 +284,14 @@ def ours(args):
         del x_full
         torch.cuda.empty_cache()
         from salient_plusplus_b200 import peer
-        ptrs = peer.exchange_partition_tables(x_local, rank, P)
+        ltab = fs.feature_table(x_local)      # resident copy, 128-byte-multiple row pitch
+        ctab = cache.device_table()
+        ptrs = peer.exchange_partition_tables(ltab.storage, rank, P)
         ptrs[rank] = 0
         tables = [None] * P
-        tables[rank] = x_local
-        fm = fs.make_feature_map(off.tolist(), rank, tables, cache.device_features(), cache.device_map(n), ptrs)
+        tables[rank] = ltab.storage
+        fm = fs.make_feature_map(off.tolist(), rank, tables, ctab.storage, cache.device_map(n), ptrs, ltab.pitch,
+                                 ctab.pitch)
 
     pipe = MiniBatchPipeline(rowptr, col32, sizes, bs, x_table=None if fm is not None else x_local, y_table=y,
                              feature_map=fm, feat_dim=f, feat_dtype=dt, split=False, depth=args.depth, device=dev)
@@ -352,6 +355,7 @@ def ours(args):
 
     # ---- e2e: public API, seeds in pinned host memory, per-step H2D + D2H ---------------------
     def make_iter(first, count):
+        tc0 = time.perf_counter()
         cfg = FastSamplerConfig(
             x_cpu=x_local if P == 1 else torch.empty((0, f), dtype=dt), x_gpu=x_local if P > 1 else torch.empty((0, f), dtype=dt),
             y=y, rowptr=rowptr, col=col32, idx=idx_host[first * bs:(first + count) * bs], batch_size=bs,
@@ -360,12 +364,22 @@ def ours(args):
             force_exact_num_batches=False, exact_num_batches=0, count_remote_frequency=False, use_cache=P > 1)
         if P > 1:
             cfg.peer_table_ptrs = ptrs
+            cfg.peer_table_pitch = ltab.pitch
+        ta = time.perf_counter()
         sampler = FastSampler(16, max(args.depth, 4), cfg)
         it = iter(sampler)
-        return (DeviceDistributedPrefetcher([dev], it) if P > 1 else DevicePrefetcher([dev], it))
+        tb = time.perf_counter()
+        r = (DeviceDistributedPrefetcher([dev], it) if P > 1 else DevicePrefetcher([dev], it))
+        if os.environ.get("SPP_DEBUG_TIMING"):
+            print("[bench] make_iter: cfg %.0f us, sampler+session %.0f us, prefetcher(first batch) %.0f us" % (
+                (ta - tc0) * 1e6, (tb - ta) * 1e6, (time.perf_counter() - tb) * 1e6), file=sys.stderr, flush=True)
+        return r
 
     for _ in make_iter(0, max(W, 3)):
         pass
+    import gc
+    gc.collect()
+    gc.freeze()  # keep a generation-2 collection (10-20 ms with torch imported) out of the timed loop
     barrier()
     prof = None
     if args.profile_e2e:
@@ -374,11 +388,21 @@ def ours(args):
         prof.enable()
     t0 = time.perf_counter()
     got, e2e_nodes = 0, 0
-    for (batch,) in make_iter(W, K):
+    lat, tl = [], t0
+    e2e_iter = make_iter(W, K)
+    t_setup = time.perf_counter() - t0
+    for (batch,) in e2e_iter:
         got += 1
         e2e_nodes += batch.x.size(0)
+        tn = time.perf_counter()
+        lat.append(tn - tl)
+        tl = tn
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    first_us = lat[0] * 1e6
+    top3 = sorted(range(len(lat)), key=lambda i: -lat[i])[:3]
+    top3 = [(i, round(lat[i] * 1e6)) for i in top3]
+    lat.sort()
     if prof is not None:
         import pstats
         prof.disable()
@@ -418,7 +442,9 @@ def ours(args):
             "e2e": {"value": round(e2e_v, 2), "unit": UNIT, "h2d_bytes_per_step": bs * 8,
                     "d2h_bytes_per_step": 8 * 32 + (8 * 18 if P > 1 else 0),
                     "gathered_GBps": round(world * e2e_nodes * row_bytes / t_e2e / 1e9, 2),
-                    "api": "FastSampler -> " + ("DeviceDistributedPrefetcher" if P > 1 else "DevicePrefetcher")},
+                    "api": "FastSampler -> " + ("DeviceDistributedPrefetcher" if P > 1 else "DevicePrefetcher"),
+                    "per_batch_us": {"p50": round(lat[len(lat) // 2] * 1e6, 1), "p90": round(lat[int(len(lat) * 0.9)] * 1e6, 1),
+                                     "max": round(lat[-1] * 1e6, 1), "first": round(first_us, 1), "setup": round(t_setup * 1e6, 1), "slowest_iters": top3}},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_gather (feature gather)", "achieved": round(achieved, 1),

@@ -56,6 +56,12 @@ uint64_t spp_launch_count(void);
 int spp_gather_rows(const void* table, int64_t row_bytes, const void* idx, int idx_is_64,
                     int64_t n_idx, const int64_t* n_idx_dev, void* out, int64_t n_out_rows,
                     void* stream);
+/* Same, for a source table whose rows are `table_pitch` bytes apart (>= row_bytes).  A resident
+ * copy with a 256-byte pitch keeps rows whose size is not a multiple of 128 bytes (ogbn-products:
+ * 200 bytes) from straddling three DRAM lines; the output stays dense ([n, row_bytes]). */
+int spp_gather_rows_pitched(const void* table, int64_t table_pitch, int64_t row_bytes,
+                            const void* idx, int idx_is_64, int64_t n_idx,
+                            const int64_t* n_idx_dev, void* out, int64_t n_out_rows, void* stream);
 
 /* RangePartitionBook + feature placement used by the partitioned gather and the split.
  * Mirrors RangePartitionBook{rank, world_size, partition_offsets}
@@ -71,6 +77,8 @@ typedef struct spp_feature_map {
   const int32_t* cache_map;             /* dense int32[N]: cache row of a node id, -1 if none  */
                                         /* (the reference keeps a dense map too,               */
                                         /*  range_partition_book.cpp:152-158); NULL = no cache */
+  int64_t table_pitch;                  /* byte pitch of tables[*] rows; 0 = dense (row_bytes) */
+  int64_t cache_pitch;                  /* byte pitch of cache_table rows; 0 = dense           */
 } spp_feature_map;
 
 /* K4+K5 -- fused partition-book translate + cache lookup + local/cached gather + P2P miss
@@ -212,6 +220,64 @@ int spp_sample_hop_fill(const spp_graph* graph_host, int hop, int32_t fanout, in
 /* n_id_out[i] = (int64) ws->n_ids[i], i < meta[NODES(hop)]  (or int32 copy if out_is_64 == 0) */
 int spp_sample_export_nids(const spp_sampler_ws* ws_host, int hop, void* n_id_out, int out_is_64,
                            int64_t max_nodes, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * One mini-batch end to end, and the native enqueue executor.
+ * Replaces the body of fast_sampler_thread (fast_sampler/fast_sampler.cpp:963-1274): sample ->
+ * (distributed split) -> feature gather -> label gather, plus the H2D copy of the seeds and the
+ * D2H copy of the size block.  The reference runs this on a pool of CPU worker threads; here the
+ * work is ~16 asynchronous CUDA calls, issued either on the caller's thread
+ * (spp_batch_enqueue) or by a per-device executor thread (spp_executor_*), so that a Python
+ * consumer never spends its own time inside the CUDA driver.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct spp_batch_job {
+  spp_graph graph;
+  spp_sampler_ws ws;
+  const int64_t* seeds_host;       /* pinned host seeds of this batch (copied H2D) or NULL      */
+  int64_t* seeds_dev;              /* device seeds (destination of the copy, or the input)      */
+  int64_t batch_size;
+  int32_t sizes[SPP_MAX_HOPS];
+  int32_t n_hops;
+  int32_t replace;
+  uint64_t rng_seed;
+  int64_t* out_rowptr[SPP_MAX_HOPS];
+  int64_t* out_col[SPP_MAX_HOPS];
+  int64_t out_col_cap[SPP_MAX_HOPS];
+  int64_t* n_id_out;               /* int64[ws.max_nodes] or NULL                               */
+  /* features: 0 = none, 1 = single (pitched) table, 2 = partitioned map (K4+K5) */
+  int32_t feature_mode;
+  int32_t do_split;                /* != 0: spp_split_by_owner with `fmap`                      */
+  int32_t use_cache;
+  int32_t _pad;
+  const void* table;
+  int64_t table_pitch;
+  int64_t row_bytes;
+  spp_feature_map fmap;
+  void* x_out;                     /* [ws.max_nodes, row_bytes]                                 */
+  const void* y_table;             /* label rows (or NULL)                                      */
+  int64_t y_row_bytes;
+  void* y_out;                     /* [batch_size, y_row_bytes]                                 */
+  int64_t* bucket_ids;             /* split outputs (do_split)                                  */
+  int64_t* perm;
+  int64_t* bucket_counts;          /* device int64[SPP_MAX_PARTS + 2]                           */
+  int32_t* split_scratch;
+  int64_t* meta_host;              /* pinned int64[SPP_META_WORDS + SPP_MAX_PARTS + 2] or NULL  */
+  void* stream;
+} spp_batch_job;
+
+/* issue every call of the job on the calling thread (asynchronous w.r.t. the GPU) */
+int spp_batch_enqueue(const spp_batch_job* job);
+
+/* executor: one worker thread bound to `device`; jobs are issued in submission order */
+void* spp_executor_create(int device);
+void spp_executor_destroy(void* executor);
+/* copies *job, returns a ticket (> 0), or 0 on error */
+uint64_t spp_executor_submit(void* executor, const spp_batch_job* job);
+/* 1: the job's GPU work has completed, 0: not yet, < 0 / cudaError: failed (spp_last_error) */
+int spp_executor_poll(void* executor, uint64_t ticket);
+/* blocks until the job's GPU work has completed; 0 or an error code */
+int spp_executor_wait(void* executor, uint64_t ticket);
 
 /* ------------------------------------------------------------------------------------------
  * Peer mapping (CUDA IPC) for the P2P gather.  Host-synchronous.

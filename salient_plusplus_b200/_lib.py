@@ -25,12 +25,14 @@ META_OVERFLOW = 24
 
 EXPORTED = [
     "spp_abi_version", "spp_last_error", "spp_launch_count",
-    "spp_gather_rows", "spp_gather_partitioned",
+    "spp_gather_rows", "spp_gather_rows_pitched", "spp_gather_partitioned",
     "spp_nid2partid", "spp_nid2localnid", "spp_nid_is_local",
     "spp_cache_build_map", "spp_nid_is_cached", "spp_nid2cachenid",
     "spp_split_scratch_words", "spp_split_by_owner",
     "spp_sampler_sizes", "spp_sample_minibatch", "spp_sample_begin", "spp_sample_hop_count",
     "spp_sample_hop_fill", "spp_sample_export_nids",
+    "spp_batch_enqueue", "spp_executor_create", "spp_executor_destroy", "spp_executor_submit",
+    "spp_executor_poll", "spp_executor_wait",
     "spp_ipc_export", "spp_ipc_import", "spp_ipc_close", "spp_enable_peer_access",
 ]
 
@@ -39,7 +41,8 @@ class FeatureMap(Structure):
     _fields_ = [("num_parts", c_int32), ("rank", c_int32),
                 ("offsets", c_int64 * (SPP_MAX_PARTS + 1)),
                 ("tables", c_void_p * SPP_MAX_PARTS),
-                ("cache_table", c_void_p), ("cache_map", c_void_p)]
+                ("cache_table", c_void_p), ("cache_map", c_void_p),
+                ("table_pitch", c_int64), ("cache_pitch", c_int64)]
 
 
 class Graph(Structure):
@@ -58,6 +61,20 @@ class SamplerSizes(Structure):
     _fields_ = [("max_nodes", c_int64), ("max_targets", c_int64), ("table_slots", c_int64),
                 ("tile_words", c_int64), ("cand_words", c_int64), ("hop_targets", c_int64 * SPP_MAX_HOPS),
                 ("hop_edges", c_int64 * SPP_MAX_HOPS)]
+
+
+class BatchJob(Structure):
+    _fields_ = [("graph", Graph), ("ws", SamplerWs),
+                ("seeds_host", c_void_p), ("seeds_dev", c_void_p), ("batch_size", c_int64),
+                ("sizes", c_int32 * SPP_MAX_HOPS), ("n_hops", c_int32), ("replace", c_int32),
+                ("rng_seed", c_uint64),
+                ("out_rowptr", c_void_p * SPP_MAX_HOPS), ("out_col", c_void_p * SPP_MAX_HOPS),
+                ("out_col_cap", c_int64 * SPP_MAX_HOPS), ("n_id_out", c_void_p),
+                ("feature_mode", c_int32), ("do_split", c_int32), ("use_cache", c_int32), ("_pad", c_int32),
+                ("table", c_void_p), ("table_pitch", c_int64), ("row_bytes", c_int64),
+                ("fmap", FeatureMap), ("x_out", c_void_p), ("y_table", c_void_p), ("y_row_bytes", c_int64),
+                ("y_out", c_void_p), ("bucket_ids", c_void_p), ("perm", c_void_p), ("bucket_counts", c_void_p),
+                ("split_scratch", c_void_p), ("meta_host", c_void_p), ("stream", c_void_p)]
 
 
 class SalientB200Error(RuntimeError):
@@ -91,6 +108,7 @@ def load() -> ctypes.CDLL:
     L.spp_last_error.restype = c_char_p
     L.spp_launch_count.restype = c_uint64
     L.spp_gather_rows.argtypes = [vp, i64, vp, ci, i64, vp, vp, i64, vp]
+    L.spp_gather_rows_pitched.argtypes = [vp, i64, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_partitioned.argtypes = [POINTER(FeatureMap), i64, vp, ci, i64, vp, vp, i64, vp, vp]
     L.spp_nid2partid.argtypes = [POINTER(i64), ci, vp, i64, vp, vp]
     L.spp_nid2localnid.argtypes = [POINTER(i64), ci, ci, vp, i64, vp, vp]
@@ -110,6 +128,15 @@ def load() -> ctypes.CDLL:
     L.spp_sample_hop_fill.argtypes = [POINTER(Graph), ci, i32, ci, c_uint64, i64, i64,
                                       POINTER(SamplerWs), vp, vp, vp]
     L.spp_sample_export_nids.argtypes = [POINTER(SamplerWs), ci, vp, ci, i64, vp]
+    L.spp_batch_enqueue.argtypes = [POINTER(BatchJob)]
+    L.spp_executor_create.restype = vp
+    L.spp_executor_create.argtypes = [ci]
+    L.spp_executor_destroy.restype = None
+    L.spp_executor_destroy.argtypes = [vp]
+    L.spp_executor_submit.restype = c_uint64
+    L.spp_executor_submit.argtypes = [vp, POINTER(BatchJob)]
+    L.spp_executor_poll.argtypes = [vp, c_uint64]
+    L.spp_executor_wait.argtypes = [vp, c_uint64]
     L.spp_ipc_export.argtypes = [vp, POINTER(c_uint8), POINTER(i64)]
     L.spp_ipc_import.argtypes = [POINTER(c_uint8), i64, POINTER(vp)]
     L.spp_ipc_close.argtypes = [vp, i64]

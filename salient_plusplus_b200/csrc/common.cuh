@@ -94,13 +94,15 @@ __device__ __forceinline__ void st_na(int* p, const int& v) {
 __device__ __forceinline__ void st_na(short* p, const short& v) { *p = v; }
 __device__ __forceinline__ void st_na(char* p, const char& v) { *p = v; }
 
+// Flag/value handshakes between CTAs of one grid: gpu-scope relaxed accesses served by L2
+// (ld.volatile / st.volatile compile to STRONG.SYS accesses, which are not needed here).
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
   uint64_t r;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
   return r;
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {

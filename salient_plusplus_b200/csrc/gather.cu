@@ -17,7 +17,7 @@ namespace spp {
 
 constexpr int kGatherThreads = 256;
 constexpr int kRows = 64;   // rows per tile
-constexpr int kUnroll = 4;  // independent vector loads in flight per thread
+constexpr int kUnroll = 8;  // independent vector loads in flight per thread
 
 struct GatherParams {
   const char* table;     // single-table flavour
@@ -25,7 +25,9 @@ struct GatherParams {
   const int64_t* n_dev;  // optional device-resident row count
   int64_t n_max;         // host-side bound (min(n_idx, n_out_rows))
   char* out;
-  int64_t row_bytes;
+  int64_t row_bytes;     // bytes copied per row (= output pitch)
+  int64_t table_pitch;   // byte pitch of the source rows (>= row_bytes; padded tables)
+  int64_t cache_pitch;
   uint32_t vpr;        // vectors per row
   uint32_t vpr_magic;  // ceil(2^32 / vpr): lc / vpr == umulhi(lc, magic) while lc * vpr < 2^32;
                        // 0 = use a real division (vpr == 1 or very wide rows)
@@ -37,9 +39,48 @@ struct GatherParams {
   unsigned long long* counters;  // [3] local / cache / peer rows (optional)
 };
 
+// Resolution of one output row's source pointer, split so that its two dependent loads (the index
+// and, for remote rows, the dense cache map) can be issued a tile ahead of their use.
+template <bool kPartitioned>
+struct RowResolver {
+  int64_t id = 0;      // node / row id (valid when `on`)
+  int p = 0;           // owner partition
+  int32_t crow = -1;   // cache row (in flight until `finish`)
+  bool on = false;
+
+  __device__ __forceinline__ void begin_lookup(const GatherParams& prm) {
+    if constexpr (kPartitioned) {
+      crow = -1;
+      if (on) {
+        p = book_partid(prm.book, id);
+        if (p != prm.book.rank && prm.cache_map != nullptr) crow = __ldg(prm.cache_map + id);
+      }
+    }
+  }
+  // returns the source pointer and the class (0 local, 1 cache, 2 peer, -1 none)
+  __device__ __forceinline__ const char* finish(const GatherParams& prm, int& cls) const {
+    cls = -1;
+    if (!on) return nullptr;
+    if constexpr (!kPartitioned) {
+      return prm.table + id * prm.table_pitch;
+    } else {
+      if (p == prm.book.rank) {
+        cls = 0;
+        return prm.tables[p] + (id - prm.book.off[p]) * prm.table_pitch;
+      }
+      if (crow >= 0) {
+        cls = 1;
+        return prm.cache_table + (int64_t)crow * prm.cache_pitch;
+      }
+      cls = 2;
+      return prm.tables[p] + (id - prm.book.off[p]) * prm.table_pitch;  // peer HBM over NVLink
+    }
+  }
+};
+
 template <typename V, bool kPartitioned, typename IdxT>
 __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant__ GatherParams prm) {
-  __shared__ const char* s_src[kRows];
+  __shared__ const char* s_src[2][kRows];
   const int tid = threadIdx.x;
   int64_t n = prm.n_max;
   if (prm.n_dev != nullptr) {
@@ -49,54 +90,60 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
   const int64_t num_tiles = (n + kRows - 1) / kRows;
   const IdxT* __restrict__ idx = reinterpret_cast<const IdxT*>(prm.idx);
   const uint32_t vpr = prm.vpr, magic = prm.vpr_magic;
+  const bool resolver = tid < kRows;  // warps 0 and 1
+  unsigned long long cnt0 = 0, cnt1 = 0, cnt2 = 0;
 
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kRows;
-    const int rows = (int)((n - row0) < kRows ? (n - row0) : kRows);
-    __syncthreads();  // previous tile's s_src fully consumed
-    if (tid < kRows) {
-      int cls = -1;
-      if (tid < rows) {
-        const int64_t id = (int64_t)idx[row0 + tid];
-        if constexpr (!kPartitioned) {
-          s_src[tid] = prm.table + id * prm.row_bytes;
-        } else {
-          const int p = book_partid(prm.book, id);
-          const char* src;
-          if (p == prm.book.rank) {
-            src = prm.tables[p] + (id - prm.book.off[p]) * prm.row_bytes;
-            cls = 0;
-          } else {
-            int32_t crow = -1;
-            if (prm.cache_map != nullptr) crow = __ldg(prm.cache_map + id);
-            if (crow >= 0) {
-              src = prm.cache_table + (int64_t)crow * prm.row_bytes;
-              cls = 1;
-            } else {
-              src = prm.tables[p] + (id - prm.book.off[p]) * prm.row_bytes;  // peer HBM (NVLink)
-              cls = 2;
-            }
-          }
-          s_src[tid] = src;
-        }
+  auto load_id = [&](int64_t tile, RowResolver<kPartitioned>& r) {
+    r.on = false;
+    if (tile < num_tiles) {
+      const int64_t row = tile * kRows + tid;
+      if (row < n) {
+        r.id = (int64_t)idx[row];
+        r.on = true;
       }
-      if constexpr (kPartitioned) {
-        if (prm.counters != nullptr) {  // warps 0,1 are fully inside this branch
-          const uint32_t m0 = __ballot_sync(kFullMask, cls == 0);
-          const uint32_t m1 = __ballot_sync(kFullMask, cls == 1);
-          const uint32_t m2 = __ballot_sync(kFullMask, cls == 2);
-          if ((tid & 31) == 0) {
-            if (m0) atomicAdd(prm.counters + 0, (unsigned long long)__popc(m0));
-            if (m1) atomicAdd(prm.counters + 1, (unsigned long long)__popc(m1));
-            if (m2) atomicAdd(prm.counters + 2, (unsigned long long)__popc(m2));
-          }
+    }
+  };
+  auto publish = [&](const RowResolver<kPartitioned>& r, int buf) {
+    int cls;
+    const char* src = r.finish(prm, cls);
+    s_src[buf][tid] = src;
+    if constexpr (kPartitioned) {
+      if (prm.counters != nullptr) {
+        const uint32_t m0 = __ballot_sync(kFullMask, cls == 0);
+        const uint32_t m1 = __ballot_sync(kFullMask, cls == 1);
+        const uint32_t m2 = __ballot_sync(kFullMask, cls == 2);
+        if ((tid & 31) == 0) {
+          cnt0 += __popc(m0);
+          cnt1 += __popc(m1);
+          cnt2 += __popc(m2);
         }
       }
     }
-    __syncthreads();
+  };
 
+  // software pipeline over this CTA's tiles: ids of tile t+2 and the cache lookups of tile t+1
+  // are in flight while tile t streams; one barrier per tile
+  RowResolver<kPartitioned> r1, r2;
+  int64_t tile = blockIdx.x;
+  if (resolver) {
+    RowResolver<kPartitioned> r0;
+    load_id(tile, r0);
+    load_id(tile + gridDim.x, r1);
+    r0.begin_lookup(prm);
+    publish(r0, 0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (; tile < num_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kRows;
+    const int rows = (int)((n - row0) < kRows ? (n - row0) : kRows);
+    if (resolver) {
+      r1.begin_lookup(prm);                       // tile t+1: id arrived a tile ago
+      load_id(tile + 2 * (int64_t)gridDim.x, r2);  // tile t+2: id load in flight
+    }
     const uint32_t chunks = (uint32_t)rows * vpr;
     V* __restrict__ dst = reinterpret_cast<V*>(prm.out + row0 * prm.row_bytes);
+    const char* const* src = s_src[buf];
     for (uint32_t base = tid; base < chunks; base += kGatherThreads * kUnroll) {
       V vals[kUnroll];
 #pragma unroll
@@ -105,7 +152,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
         if (lc < chunks) {
           const uint32_t r = magic ? __umulhi(lc, magic) : lc / vpr;
           const uint32_t v = lc - r * vpr;
-          vals[u] = ld_nc_na(reinterpret_cast<const V*>(s_src[r]) + v);
+          vals[u] = ld_nc_na(reinterpret_cast<const V*>(src[r]) + v);
         }
       }
 #pragma unroll
@@ -114,7 +161,29 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
         if (lc < chunks) st_na(dst + lc, vals[u]);
       }
     }
+    if (resolver) {
+      publish(r1, buf ^ 1);
+      r1 = r2;
+    }
+    __syncthreads();
+    buf ^= 1;
   }
+  if constexpr (kPartitioned) {
+    if (prm.counters != nullptr && resolver && (tid & 31) == 0) {
+      if (cnt0) atomicAdd(prm.counters + 0, cnt0);
+      if (cnt1) atomicAdd(prm.counters + 1, cnt1);
+      if (cnt2) atomicAdd(prm.counters + 2, cnt2);
+    }
+  }
+}
+
+static int gather_ctas_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("SPP_GATHER_CTAS_PER_SM");
+    v = (e && atoi(e) > 0) ? atoi(e) : 4;
+  }
+  return v;
 }
 
 // Experiment hook: SPP_L2_FETCH_GRANULARITY=32|64|128 sets cudaLimitMaxL2FetchGranularity once.
@@ -136,7 +205,9 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
   const bool magic_ok = prm.vpr > 1 && (uint64_t)kRows * prm.vpr * prm.vpr < (1ull << 32);
   prm.vpr_magic = magic_ok ? (uint32_t)(((1ull << 32) + prm.vpr - 1) / prm.vpr) : 0u;
   const int64_t tiles = ceil_div(prm.n_max, kRows);
-  const int64_t max_ctas = (int64_t)num_sms() * 8;
+  // 4 CTAs / SM x 8 loads in flight per thread saturate HBM and leave half of every SM's thread
+  // slots to the latency-bound sampler kernels of the other in-flight mini-batches
+  const int64_t max_ctas = (int64_t)num_sms() * gather_ctas_per_sm();
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
 #define SPP_GATHER_LAUNCH(V)                                                                    \
   do {                                                                                          \
@@ -169,8 +240,14 @@ extern "C" {
 
 int spp_gather_rows(const void* table, int64_t row_bytes, const void* idx, int idx_is_64, int64_t n_idx,
                     const int64_t* n_idx_dev, void* out, int64_t n_out_rows, void* stream) {
+  return spp_gather_rows_pitched(table, row_bytes, row_bytes, idx, idx_is_64, n_idx, n_idx_dev, out, n_out_rows, stream);
+}
+
+int spp_gather_rows_pitched(const void* table, int64_t table_pitch, int64_t row_bytes, const void* idx, int idx_is_64,
+                            int64_t n_idx, const int64_t* n_idx_dev, void* out, int64_t n_out_rows, void* stream) {
   using namespace spp;
   if (row_bytes <= 0) return fail(SPP_EINVAL, "spp_gather_rows: row_bytes must be positive");
+  if (table_pitch < row_bytes) return fail(SPP_EINVAL, "spp_gather_rows: table pitch smaller than the row");
   int64_t n = n_idx < n_out_rows ? n_idx : n_out_rows;
   if (n <= 0) return 0;
   if (!table || !idx || !out) return fail(SPP_EINVAL, "spp_gather_rows: null pointer");
@@ -181,7 +258,8 @@ int spp_gather_rows(const void* table, int64_t row_bytes, const void* idx, int i
   prm.n_max = n;
   prm.out = (char*)out;
   prm.row_bytes = row_bytes;
-  int vb = pick_vec_bytes(row_bytes, (uintptr_t)table | (uintptr_t)out);
+  prm.table_pitch = table_pitch;
+  int vb = pick_vec_bytes(row_bytes, (uintptr_t)table | (uintptr_t)out | (uintptr_t)table_pitch);
   return launch_gather<false>(prm, vb, idx_is_64, (cudaStream_t)stream);
 }
 
@@ -204,9 +282,13 @@ int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const vo
   prm.n_max = n;
   prm.out = (char*)out;
   prm.row_bytes = row_bytes;
+  prm.table_pitch = m->table_pitch > 0 ? m->table_pitch : row_bytes;
+  prm.cache_pitch = m->cache_pitch > 0 ? m->cache_pitch : row_bytes;
+  if (prm.table_pitch < row_bytes || prm.cache_pitch < row_bytes)
+    return fail(SPP_EINVAL, "spp_gather_partitioned: pitch smaller than the row");
   prm.book.num_parts = m->num_parts;
   prm.book.rank = m->rank;
-  uintptr_t align = (uintptr_t)out;
+  uintptr_t align = (uintptr_t)out | (uintptr_t)prm.table_pitch | (uintptr_t)prm.cache_pitch;
   for (int p = 0; p <= SPP_MAX_PARTS; ++p) prm.book.off[p] = p <= m->num_parts ? m->offsets[p] : m->offsets[m->num_parts];
   for (int p = 0; p < m->num_parts; ++p) {
     if (m->offsets[p + 1] < m->offsets[p]) return fail(SPP_EINVAL, "spp_gather_partitioned: offsets not sorted");

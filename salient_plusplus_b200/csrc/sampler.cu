@@ -20,6 +20,7 @@
 //
 // Hash entry: 64 bits = { key + 1 , ~local } ; empty = 0, so the table is cleared by a memset.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -367,18 +368,19 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact(const __grid_const
     if (tile >= num_tiles) break;
     const int64_t p0 = tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
     uint32_t slot[kScanItems];
+    uint64_t ent[kScanItems];
     uint32_t flags = 0, cnt = 0;
+    const uint64_t* tab64 = reinterpret_cast<const uint64_t*>(prm.tab.w);
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) slot[q] = (p0 + q < E) ? (uint32_t)prm.out_col[p0 + q] : 0u;
+#pragma unroll
+    for (int q = 0; q < kScanItems; ++q) ent[q] = __ldcg(tab64 + slot[q]);
 #pragma unroll
     for (int q = 0; q < kScanItems; ++q) {
       const int64_t p = p0 + q;
-      slot[q] = 0;
-      if (p < E) {
-        slot[q] = (uint32_t)prm.out_col[p];
-        const uint32_t enc = __ldcg(prm.tab.w + 2 * (size_t)slot[q] + 1);
-        if (enc == ~(Tbase + (uint32_t)p)) {
-          flags |= 1u << q;
-          ++cnt;
-        }
+      if (p < E && (uint32_t)(ent[q] >> 32) == ~(Tbase + (uint32_t)p)) {
+        flags |= 1u << q;
+        ++cnt;
       }
     }
     uint64_t total;
@@ -390,9 +392,8 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact(const __grid_const
       if (flags & (1u << q)) {
         const int64_t L = T + (int64_t)r;
         if (L < prm.max_nodes) {
-          uint32_t* ent = prm.tab.w + 2 * (size_t)slot[q];
-          prm.n_ids[L] = (int32_t)(__ldcg(ent) - 1u);
-          __stcg(ent + 1, ~(uint32_t)L);
+          prm.n_ids[L] = (int32_t)((uint32_t)ent[q] - 1u);
+          __stcg(prm.tab.w + 2 * (size_t)slot[q] + 1, ~(uint32_t)L);
         }
         ++r;
       }
@@ -592,7 +593,10 @@ struct FusedParams {
   uint32_t epoch;    // tag of this launch's tile aggregates
 };
 
-template <int G, bool kCol64>
+// Lane groups of exactly k lanes (32 / k targets per warp) and a three-stage software pipeline
+// per group: [n_ids -> rowptr of target t+2 / t+1] | [picks + col load of target t+1] | [table CAS +
+// atomicMax of target t], so the random col read and the L2 atomics of consecutive targets overlap.
+template <bool kCol64>
 __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __grid_constant__ FusedParams fp) {
   const HopParams& prm = fp.h;
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
@@ -602,69 +606,100 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __gri
     if (blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_OVERFLOW] = 1;
     return;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) prm.tile_state[0] = 0;  // ticket counter of k_hop_compact_fused
   const uint32_t Tbase = (uint32_t)T;
   const int lane = threadIdx.x & 31;
-  const int gl = lane & (G - 1);
-  const int gbase = lane & ~(G - 1);
-  constexpr int kGroupsPerWarp = 32 / G;
+  const int gpw = 32 / k;                 // groups (targets) per warp
+  const int g = lane / k;                 // my group
+  const bool lane_on = g < gpw;           // tail lanes of the warp idle when 32 % k != 0
+  const int gl = lane - g * k;            // lane inside the group
+  const int gbase = lane_on ? g * k : 0;
+  const uint32_t kmask = k == 32 ? 0xffffffffu : ((1u << k) - 1u);
   const int64_t warp_global = ((int64_t)blockIdx.x * kSampleThreads + threadIdx.x) >> 5;
-  const int64_t stride = (((int64_t)gridDim.x * kSampleThreads) >> 5) * kGroupsPerWarp;
+  const int64_t stride = (((int64_t)gridDim.x * kSampleThreads) >> 5) * gpw;
 
-  // software pipeline: the (node, rowptr pair) of the next target is in flight while the current
-  // target's col reads and table atomics are outstanding
-  int64_t i = warp_global * kGroupsPerWarp + (lane / G);
+  int64_t i0 = warp_global * gpw;  // warp-uniform index of the warp's first target this round
+  // stage A registers: rowptr pair of target (i0 + g), node id of target (i0 + stride + g)
   int64_t nstart = 0, nend = 0;
-  if (i < T) {
-    const int32_t n = prm.n_ids[i];
-    nstart = __ldg(prm.rowptr + n);
-    nend = __ldg(prm.rowptr + n + 1);
-  }
-  for (int64_t i0 = warp_global * kGroupsPerWarp; i0 < T; i0 += stride) {
-    const bool valid = i < T;
-    const int64_t start = nstart;
-    const int32_t deg = (int32_t)(nend - nstart);
-    const int64_t icur = i;
-    i += stride;
-    if (i < T) {
+  int32_t n_next = 0;
+  {
+    const int64_t i = i0 + g;
+    if (lane_on && i < T) {
       const int32_t n = prm.n_ids[i];
       nstart = __ldg(prm.rowptr + n);
       nend = __ldg(prm.rowptr + n + 1);
     }
-    const bool need = valid && deg > k;
-    const int32_t basej = deg - k;
-    uint32_t myr = 0, mypick = 0xffffffffu;
-    if (need && gl < k)
-      myr = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)icur, (uint32_t)gl), (uint32_t)(basej + gl) + 1u);
-    if (__any_sync(kFullMask, need)) {
+    if (lane_on && i + stride < T) n_next = prm.n_ids[i + stride];
+  }
+  // stage C registers (candidate whose col value is in flight / has landed)
+  bool c_valid = false;
+  int32_t c_node = 0;
+  uint32_t c_v = 0;
+
+  while (true) {
+    const bool have = i0 < T;  // warp-uniform
+    bool b_valid = false;
+    int32_t b_node = 0;
+    uint32_t b_v = 0;
+    if (have) {
+      // ---- stage B: picks of target i0 + g, col load issued (not consumed here) ----------------
+      const int64_t i = i0 + g;
+      const bool valid = lane_on && i < T;
+      const int64_t start = nstart;
+      const int32_t deg = (int32_t)(nend - nstart);
+      const bool need = valid && deg > k;
+      const int32_t basej = deg - k;
+      uint32_t myr = 0, mypick = 0xffffffffu;
+      if (need) myr = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)gl), (uint32_t)(basej + gl) + 1u);
+      if (__any_sync(kFullMask, need)) {
 #pragma unroll 1
-      for (int s = 0; s < k; ++s) {  // Floyd: t uniform on [0, basej+s]; taken already -> basej+s
-        const uint32_t t = __shfl_sync(kFullMask, myr, gbase + s);
-        const uint32_t b = __ballot_sync(kFullMask, need && gl < s && mypick == t);
-        const uint32_t gm = (G == 32) ? b : ((b >> gbase) & ((1u << G) - 1u));
-        if (gl == s) mypick = gm ? (uint32_t)(basej + s) : t;
+        for (int s = 0; s < k; ++s) {  // Floyd: t uniform on [0, basej+s]; taken already -> basej+s
+          const uint32_t t = __shfl_sync(kFullMask, myr, gbase + s);
+          const uint32_t b = __ballot_sync(kFullMask, need && gl < s && mypick == t);
+          if (gl == s) mypick = ((b >> gbase) & kmask) ? (uint32_t)(basej + s) : t;
+        }
       }
-    }
-    const int32_t c = deg < k ? deg : k;
-    if (valid && gl < k) {
-      const int64_t v = icur * k + gl;
-      uint32_t slot = kInvalidCand;
-      if (gl < c) {
-        const uint32_t pick = need ? mypick : (uint32_t)gl;
-        const int32_t node = load_col<kCol64>(prm.col, start + pick);
-        slot = table_insert_optimistic(prm.tab, node);
-        atomicMax(prm.tab.w + 2 * (size_t)slot + 1, ~(Tbase + (uint32_t)v));
+      if (valid) {
+        const int32_t c = deg < k ? deg : k;
+        b_v = (uint32_t)(i * k + gl);
+        if (gl < c) {
+          const uint32_t pick = need ? mypick : (uint32_t)gl;
+          b_node = load_col<kCol64>(prm.col, start + pick);
+          b_valid = true;
+        } else {
+          fp.cand[b_v] = kInvalidCand;
+        }
       }
-      fp.cand[v] = slot;
+      // ---- stage A: rowptr of the next target, node id of the one after -----------------------
+      const int64_t in = i + stride;
+      if (lane_on && in < T) {
+        nstart = __ldg(prm.rowptr + n_next);
+        nend = __ldg(prm.rowptr + n_next + 1);
+      }
+      if (lane_on && in + stride < T) n_next = prm.n_ids[in + stride];
     }
+    // ---- stage C: insert the previous round's candidate ------------------------------------------
+    if (c_valid) {
+      const uint32_t slot = table_insert_optimistic(prm.tab, c_node);
+      atomicMax(prm.tab.w + 2 * (size_t)slot + 1, ~(Tbase + c_v));
+      fp.cand[c_v] = slot;
+    }
+    if (!have) break;
+    c_valid = b_valid;
+    c_node = b_node;
+    c_v = b_v;
+    i0 += stride;
   }
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid_constant__ FusedParams fp) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
-  __shared__ unsigned long long s_red[kScanThreads / 32];
   __shared__ unsigned long long s_base;
   __shared__ int64_t s_tile;
   const HopParams& prm = fp.h;
+  // first ticket: issued at once, in flight together with the meta loads.  The ticket counter
+  // (tile_state[0]) was zeroed by this hop's k_hop_sample_fused, which precedes us in stream order.
+  if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd((unsigned long long*)prm.tile_state, 1ull);
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
   if (T > prm.max_targets) T = prm.max_targets;
   const int k = prm.fanout;
@@ -672,8 +707,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
   if (V > fp.cand_cap || (uint64_t)T * (uint64_t)(k + 1) >= 0xFFFFFFF0ull) V = 0;  // overflow flagged by the sampler
   const uint32_t Tbase = (uint32_t)T;
   const int64_t num_tiles = (V + kFusedTile - 1) / kFusedTile;
-  unsigned long long* ctr = (unsigned long long*)prm.tile_state;        // [0] dynamic tile counter
-  unsigned long long* done = ctr + 1;                                   // [1] CTAs finished
+  unsigned long long* ctr = (unsigned long long*)prm.tile_state;        // [0] ticket counter
   uint64_t* agg = prm.tile_state + 2;                                   // [2 + t] epoch | kept | new
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -685,21 +719,32 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
   }
   // rows without a virtual position (V == 0 because of an overflow) are left untouched
   while (true) {
-    if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ctr, 1ull);
     __syncthreads();
     const int64_t tile = s_tile;
     if (tile >= num_tiles) break;
     const int64_t v0 = tile * kFusedTile + (int64_t)threadIdx.x * kFusedItems;
     uint32_t slot[kFusedItems];
+    uint64_t ent[kFusedItems];
     uint32_t keptm = 0, newm = 0;
+    if (v0 + kFusedItems <= V) {  // 32-byte aligned run of candidates: two 128-bit loads
+      const uint4 a = __ldcg(reinterpret_cast<const uint4*>(fp.cand + v0));
+      const uint4 b = __ldcg(reinterpret_cast<const uint4*>(fp.cand + v0) + 1);
+      slot[0] = a.x; slot[1] = a.y; slot[2] = a.z; slot[3] = a.w;
+      slot[4] = b.x; slot[5] = b.y; slot[6] = b.z; slot[7] = b.w;
+    } else {
 #pragma unroll
-    for (int q = 0; q < kFusedItems; ++q) slot[q] = (v0 + q < V) ? fp.cand[v0 + q] : kInvalidCand;
+      for (int q = 0; q < kFusedItems; ++q) slot[q] = (v0 + q < V) ? fp.cand[v0 + q] : kInvalidCand;
+    }
+    // all table entries {key+1, ~local} of the thread's candidates as independent 64-bit loads
+    // (the key is needed later for n_ids; loading it here keeps it off the dependent path)
+    const uint64_t* tab64 = reinterpret_cast<const uint64_t*>(prm.tab.w);
+#pragma unroll
+    for (int q = 0; q < kFusedItems; ++q) ent[q] = __ldcg(tab64 + (slot[q] != kInvalidCand ? slot[q] : 0u));
 #pragma unroll
     for (int q = 0; q < kFusedItems; ++q) {
       if (slot[q] != kInvalidCand) {
         keptm |= 1u << q;
-        const uint32_t enc = __ldcg(prm.tab.w + 2 * (size_t)slot[q] + 1);
-        if (enc == ~(Tbase + (uint32_t)(v0 + q))) newm |= 1u << q;
+        if ((uint32_t)(ent[q] >> 32) == ~(Tbase + (uint32_t)(v0 + q))) newm |= 1u << q;
       }
     }
     // packed (kept << 16 | new) block scan: per-tile sums are <= 2048 each
@@ -716,24 +761,26 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
     }
     const uint32_t texcl = wbase + inc - mine;
     if (threadIdx.x == 0) st_volatile_u64(agg + tile, ((uint64_t)fp.epoch << 32) | (uint64_t)total);
-    // sum of the aggregates of every earlier tile (published independently of their own waits)
-    unsigned long long acc = 0;  // kept in the high 32 bits, new in the low 32 bits
-    for (int64_t t = threadIdx.x; t < tile; t += kScanThreads) {
-      uint64_t w;
-      do {
-        w = ld_volatile_u64(agg + t);
-      } while ((uint32_t)(w >> 32) != fp.epoch);
-      acc += ((unsigned long long)((uint32_t)w >> 16) << 32) | (unsigned long long)((uint32_t)w & 0xffffu);
-    }
+    // Sum of the aggregates of every earlier tile (each is published independently of its owner's
+    // own wait, so there is no serial chain).  Only warp 0 polls -- 32 flags per round, with a
+    // back-off -- so that waiting CTAs do not flood L2 with flag reads while the earlier tiles
+    // are still loading their table entries (measured: 256 pollers per CTA tripled the kernel time).
+    if (warp == 0) {
+      unsigned long long acc = 0;  // kept in the high 32 bits, new in the low 32 bits
+      for (int64_t t0 = 0; t0 < tile; t0 += 32) {
+        const int64_t t = t0 + lane;
+        if (t < tile) {
+          uint64_t w = ld_volatile_u64(agg + t);
+          while ((uint32_t)(w >> 32) != fp.epoch) {
+            __nanosleep(64);
+            w = ld_volatile_u64(agg + t);
+          }
+          acc += ((unsigned long long)((uint32_t)w >> 16) << 32) | (unsigned long long)((uint32_t)w & 0xffffu);
+        }
+      }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
-    if (lane == 0) s_red[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long b = 0;
-#pragma unroll
-      for (int w = 0; w < kScanThreads / 32; ++w) b += s_red[w];
-      s_base = b;
+      for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
+      if (lane == 0) s_base = acc;
     }
     __syncthreads();
     const unsigned long long base = s_base;
@@ -749,9 +796,8 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
         if (newm & (1u << q)) {
           const int64_t L = T + (int64_t)new_run;
           if (L < prm.max_nodes) {
-            uint32_t* ent = prm.tab.w + 2 * (size_t)slot[q];
-            prm.n_ids[L] = (int32_t)(__ldcg(ent) - 1u);
-            __stcg(ent + 1, ~(uint32_t)L);
+            prm.n_ids[L] = (int32_t)((uint32_t)ent[q] - 1u);
+            __stcg(prm.tab.w + 2 * (size_t)slot[q] + 1, ~(uint32_t)L);
           }
           ++new_run;
         }
@@ -773,15 +819,9 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
       prm.meta[SPP_META_EDGES(prm.hop)] = (int64_t)kept_total;
       prm.meta[SPP_META_NODES(prm.hop + 1)] = S;
     }
-    __syncthreads();  // s_tile / s_base reuse
-  }
-  // the last CTA out re-arms the counters for the next launch on this workspace
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(done, 1ull) == (unsigned long long)gridDim.x - 1ull) {
-      *ctr = 0ull;
-      *done = 0ull;
-    }
+    if (num_tiles <= (int64_t)gridDim.x) break;  // every tile has its own CTA: no second ticket
+    __syncthreads();                               // s_tile / s_base consumed
+    if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ctr, 1ull);
   }
 }
 
@@ -1011,23 +1051,19 @@ static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_
   fp.epoch = (g_epoch.fetch_add(1, std::memory_order_relaxed) % 0x3FFFFFFFu) + 1u;
   const bool c64 = g->col_is_64 != 0;
   const int sms = num_sms();
-  const int G = fanout <= 4 ? 4 : fanout <= 8 ? 8 : fanout <= 16 ? 16 : 32;
+  const int G = fanout <= 4 ? 4 : fanout <= 8 ? 8 : fanout <= 16 ? 16 : 32;  // relabel/sort groups (power of two)
+  const int64_t cap = (int64_t)sms * 8;
+  {
+    const int gpw = 32 / fanout;
+    int64_t warps = ceil_div(fp.h.max_targets > 0 ? fp.h.max_targets : 1, gpw);
+    int64_t ctas = ceil_div(warps, kSampleThreads / 32);
+    const int sgrid = (int)(ctas < cap ? ctas : cap);
+    if (c64) k_hop_sample_fused<true><<<sgrid, kSampleThreads, 0, st>>>(fp);
+    else k_hop_sample_fused<false><<<sgrid, kSampleThreads, 0, st>>>(fp);
+  }
   int64_t warps = ceil_div(fp.h.max_targets > 0 ? fp.h.max_targets : 1, 32 / G);
   int64_t ctas = ceil_div(warps, kSampleThreads / 32);
-  int64_t cap = (int64_t)sms * 8;
   const int grid = (int)(ctas < cap ? ctas : cap);
-#define SPP_FUSED_SAMPLE(GG)                                                                   \
-  do {                                                                                          \
-    if (c64) k_hop_sample_fused<GG, true><<<grid, kSampleThreads, 0, st>>>(fp);                 \
-    else k_hop_sample_fused<GG, false><<<grid, kSampleThreads, 0, st>>>(fp);                    \
-  } while (0)
-  switch (G) {
-    case 4: SPP_FUSED_SAMPLE(4); break;
-    case 8: SPP_FUSED_SAMPLE(8); break;
-    case 16: SPP_FUSED_SAMPLE(16); break;
-    default: SPP_FUSED_SAMPLE(32); break;
-  }
-#undef SPP_FUSED_SAMPLE
   SPP_KERNEL_CHECK("k_hop_sample_fused");
   const int64_t scap = (int64_t)sms * 6;
   k_hop_compact_fused<<<(int)(tiles < scap ? tiles : scap), kScanThreads, 0, st>>>(fp);

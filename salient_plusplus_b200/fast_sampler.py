@@ -30,7 +30,7 @@ import torch
 
 from . import _lib
 from ._lib import (META_EDGES0, META_OVERFLOW, SPP_MAX_HOPS, SPP_MAX_PARTS, SPP_META_WORDS,
-                   FeatureMap, Graph, SalientB200Error, SamplerSizes, SamplerWs, check)
+                   BatchJob, FeatureMap, Graph, SalientB200Error, SamplerSizes, SamplerWs, check)
 
 __all__ = ["Config", "Session", "ProtoDistributedBatch", "RangePartitionBook", "Cache", "sample_adj",
            "multilayer_sample", "full_sample", "serial_index", "to_row_major"]
@@ -78,6 +78,56 @@ def _resident(t: torch.Tensor, dtype: Optional[torch.dtype] = None, tag: str = "
 
 def clear_resident_cache() -> None:
     _RESIDENT.clear()
+
+
+class _FeatureTable:
+    """A feature matrix resident in HBM.  Rows whose byte size is not a multiple of 128 would
+    straddle up to three 128-byte DRAM lines when gathered at random (ogbn-products: 200-byte
+    rows -> 2.5 lines = 320 bytes fetched per row, measured with ncu), so the resident copy is laid
+    out with a row pitch rounded up to 128 bytes when that costs at most 1/3 extra memory
+    (``SPP_PAD_FEATURE_ROWS=0`` disables).  The gather output stays dense."""
+    __slots__ = ("storage", "ptr", "pitch", "row_bytes", "dim", "dtype", "rows", "_src")
+
+    def __init__(self, x: torch.Tensor):
+        dev = _device()
+        self.dim, self.dtype, self.rows = x.size(-1), x.dtype, x.size(0)
+        es = x.element_size()
+        self.row_bytes = self.dim * es
+        pitch = self.row_bytes
+        if (os.environ.get("SPP_PAD_FEATURE_ROWS", "1") != "0" and self.row_bytes % 128 != 0
+                and self.row_bytes >= 96):
+            cand = (self.row_bytes + 127) // 128 * 128
+            if cand * 3 <= self.row_bytes * 4 and cand % es == 0:
+                pitch = cand
+        self.pitch = pitch
+        self._src = x
+        if pitch == self.row_bytes:
+            self.storage = _resident(x, None, "features")
+        else:
+            st = torch.empty((self.rows, pitch // es), dtype=x.dtype, device=dev)
+            chunk = max(1, (256 << 20) // max(self.row_bytes, 1))
+            for r0 in range(0, self.rows, chunk):
+                r1 = min(self.rows, r0 + chunk)
+                st[r0:r1, :self.dim].copy_(x[r0:r1], non_blocking=False)
+            self.storage = st
+        self.ptr = self.storage.data_ptr()
+
+
+_FEATURE_TABLES: "OrderedDict[tuple, _FeatureTable]" = OrderedDict()
+
+
+def feature_table(x: torch.Tensor) -> _FeatureTable:
+    key = (x.data_ptr(), tuple(x.shape), x.dtype, x._version, x.device.type,
+           torch.cuda.current_device() if torch.cuda.is_available() else -1,
+           os.environ.get("SPP_PAD_FEATURE_ROWS", "1"))
+    t = _FEATURE_TABLES.get(key)
+    if t is None:
+        t = _FEATURE_TABLES[key] = _FeatureTable(x)
+        while len(_FEATURE_TABLES) > 8:
+            _FEATURE_TABLES.popitem(last=False)
+    else:
+        _FEATURE_TABLES.move_to_end(key)
+    return t
 
 
 class _DeviceGraph:
@@ -405,6 +455,11 @@ class Cache:
     def device_features(self) -> torch.Tensor:
         return _resident(self._cached_features, None, "cache_features")
 
+    def device_table(self) -> Optional["_FeatureTable"]:
+        if self._cached_features.dim() != 2 or self._cached_features.numel() == 0:
+            return None
+        return feature_table(self._cached_features)
+
     def _lookup(self, nids: torch.Tensor, fn, dtype):
         device = _device()
         ids = nids.to(device=device, dtype=torch.int64).contiguous()
@@ -423,7 +478,8 @@ class Cache:
 
 def make_feature_map(offsets: Sequence[int], rank: int, tables: Sequence[Optional[torch.Tensor]],
                      cache_table: Optional[torch.Tensor] = None, cache_map: Optional[torch.Tensor] = None,
-                     table_ptrs: Optional[Sequence[int]] = None) -> FeatureMap:
+                     table_ptrs: Optional[Sequence[int]] = None, table_pitch: int = 0,
+                     cache_pitch: int = 0) -> FeatureMap:
     """Fill the C ``spp_feature_map``: ``tables[p]`` are device tensors (local partitions) and/or
     ``table_ptrs[p]`` raw device pointers of IPC-mapped peer partitions."""
     P = len(offsets) - 1
@@ -441,6 +497,8 @@ def make_feature_map(offsets: Sequence[int], rank: int, tables: Sequence[Optiona
         fm.tables[p] = ptr
     fm.cache_table = cache_table.data_ptr() if cache_table is not None and cache_table.numel() > 0 else None
     fm.cache_map = cache_map.data_ptr() if (cache_map is not None and fm.cache_table) else None
+    fm.table_pitch = int(table_pitch)
+    fm.cache_pitch = int(cache_pitch)
     return fm
 
 
@@ -475,6 +533,7 @@ class Config:
         # extensions (not in the reference)
         self.partition_tables = None
         self.peer_table_ptrs = None
+        self.peer_table_pitch = 0
         self.fused_gather = True
 
 
@@ -540,12 +599,27 @@ class _Slot:
         self.event = torch.cuda.Event()
         self.meta_host = torch.empty(SPP_META_WORDS + SPP_MAX_PARTS + 2, dtype=torch.int64).pin_memory()
         self.seeds = torch.empty(max(max_bs, 1), dtype=torch.int64, device=device)
+        self.seeds_host = torch.empty(max(max_bs, 1), dtype=torch.int64).pin_memory()  # H2D staging
         if split_words:
             self.split_scratch = torch.empty(split_words, dtype=torch.int32, device=device)
             self.counts = torch.zeros(SPP_MAX_PARTS + 2, dtype=torch.int64, device=device)
         self.job = None
-        self.c_rp = (c_vp * SPP_MAX_HOPS)()
-        self.c_cp = (c_vp * SPP_MAX_HOPS)()
+        self.ticket = None
+        self.cjob = BatchJob()
+
+
+_EXECUTORS: dict = {}
+
+
+def _executor(device_index: int):
+    """The native enqueue executor of a device (one worker thread inside libsalient_b200)."""
+    ex = _EXECUTORS.get(device_index)
+    if ex is None:
+        ex = _lib.load().spp_executor_create(device_index)
+        if not ex:
+            raise SalientB200Error("spp_executor_create failed: " + _lib.load().spp_last_error().decode())
+        _EXECUTORS[device_index] = ex
+    return ex
 
 
 _SLOT_POOL: dict = {}
@@ -570,6 +644,7 @@ class Session:
     def __init__(self, num_threads: int, max_items_in_queue: int, config: Config):
         if max_items_in_queue <= 0:
             raise RuntimeError(f"max_items_in_queue ({max_items_in_queue}) must be positive")
+        _t = [time.perf_counter()] if os.environ.get("SPP_DEBUG_TIMING") else None
         self._config = copy.copy(config)  # copied by value like fast_sampler.cpp:541-542
         cfg = self._config
         self._device = _device()
@@ -580,11 +655,13 @@ class Session:
         self._g = _DeviceGraph.get(cfg.rowptr, cfg.col)
         # Seeds: a device-resident idx is used in place; a host idx (what the reference's driver
         # passes) is pinned once and each batch's slice is copied H2D on that batch's stream.
+        # (each batch's slice is staged through the slot's pinned buffer: the reference's driver
+        # passes pageable tensors, and pinning a fresh idx every epoch would cost milliseconds)
         idx = cfg.idx.to(torch.int64).contiguous()
         if idx.is_cuda:
             self._idx, self._idx_host = idx, None
         else:
-            self._idx, self._idx_host = None, (idx.pin_memory() if idx.numel() else idx)
+            self._idx, self._idx_host = None, idx
         self._ranges = _batch_ranges(idx.numel(), cfg)
         self._num_total = len(self._ranges)
         self._num_consumed = 0
@@ -595,7 +672,9 @@ class Session:
         self._y = _resident(cfg.y, None, "y") if cfg.y is not None else None
         if self._y is not None and self._y.dim() == 1:
             self._y = self._y.view(-1, 1)
+        if _t: _t.append(time.perf_counter())
         self._setup_features()
+        if _t: _t.append(time.perf_counter())
         self._row_bytes = self._feat_shape[0] * torch.empty(0, dtype=self._feat_shape[1]).element_size()
         max_bs = max((e - s for s, e in self._ranges), default=0)
         self._sz = _sampler_sizes(max_bs, self._sizes, self._g)
@@ -620,8 +699,12 @@ class Session:
         if cfg.distributed:
             o += 3 * int(sz.max_nodes)  # n_id, bucket_ids, perm
         self._arena_words = max(o, 1)
-        self._c_sizes = (ctypes.c_int32 * max(L, 1))(*self._sizes)
-        self._c_caps = (ctypes.c_int64 * max(L, 1))(*[int(sz.hop_edges[h]) for h in range(L)])
+        self._executor = None
+        if not self._full and os.environ.get("SPP_EXECUTOR", "1") != "0":
+            self._executor = _executor(self._device.index)
+        if not self._full:
+            for s_ in self._slots:
+                self._init_job(s_)
         self._free = deque(self._slots)
         self._pending: deque = deque()
         self._freq = None
@@ -633,8 +716,13 @@ class Session:
         cur = torch.cuda.current_stream()
         for s in self._slots:
             s.stream.wait_stream(cur)
+        if _t: _t.append(time.perf_counter())
         while self._free and self._next < self._num_total:
             self._enqueue()
+        if _t:
+            _t.append(time.perf_counter())
+            print("[spp] Session init us: graph/idx %.0f features %.0f slots/jobs %.0f first enqueues %.0f" % tuple(
+                (b - a) * 1e6 for a, b in zip(_t[:-1], _t[1:])), flush=True)
 
     # -- set-up -------------------------------------------------------------------------------
     def _setup_features(self):
@@ -645,7 +733,7 @@ class Session:
         if not cfg.distributed:
             x = cfg.x_cpu
             if x is not None and x.dim() == 2 and x.numel() > 0:
-                self._x_table = _resident(x, None, "x")
+                self._x_table = feature_table(x)
             self._feat_shape = (x.size(-1), x.dtype) if x is not None and x.dim() == 2 else (0, torch.float16)
             return
         book = cfg.partition_book
@@ -688,30 +776,76 @@ class Session:
         self._split_fm = make_feature_map(off, self._rank, [None] * self._P)
         if self._use_cache:
             self._split_fm.cache_map = self._cache_map.data_ptr()
-        # full map (tables of every partition) for the fused gather, when reachable
+        # full map (tables of every partition) for the fused gather, when reachable.  The tables
+        # are _FeatureTable objects: every rank derives the same row pitch from (F, dtype).
         if cfg.fused_gather and local is not None:
+            ltab = feature_table(local)
             tables = [None] * self._P
             ptrs = [0] * self._P
             if cfg.partition_tables is not None:
-                tables = [(_resident(t, None, f"part{p}") if t is not None else None)
-                          for p, t in enumerate(cfg.partition_tables)]
+                for p, t in enumerate(cfg.partition_tables):
+                    if t is not None and p != self._rank:
+                        ft = feature_table(t)
+                        if ft.pitch != ltab.pitch:
+                            raise RuntimeError("partition tables disagree on the feature row size")
+                        tables[p] = ft.storage
             if cfg.peer_table_ptrs is not None:
                 ptrs = [int(v or 0) for v in cfg.peer_table_ptrs]
-            tables[self._rank] = local
+                pitch = int(getattr(cfg, "peer_table_pitch", 0) or 0) or ltab.row_bytes
+                if pitch != ltab.pitch:
+                    raise RuntimeError(f"peer tables have row pitch {pitch}, local table {ltab.pitch}")
+            tables[self._rank] = ltab.storage
             ptrs[self._rank] = 0
             reachable = all((tables[p] is not None) or ptrs[p] or off[p + 1] == off[p] for p in range(self._P))
             if not reachable:
                 from . import peer
-                got = peer.exchange_partition_tables(local, self._rank, self._P)
+                got = peer.exchange_partition_tables(ltab.storage, self._rank, self._P)
                 if got is not None:
                     ptrs = got
                     ptrs[self._rank] = 0
                     reachable = True
             if reachable:
-                self._part_tables = tables  # keep alive
-                self._fm = make_feature_map(off, self._rank, tables, self._cache_feats, self._cache_map, ptrs)
+                self._part_tables = (tables, ltab)  # keep alive
+                ctab = cfg.cache.device_table() if self._use_cache else None
+                self._fm = make_feature_map(off, self._rank, tables, ctab.storage if ctab else None,
+                                            self._cache_map, ptrs, ltab.pitch, ctab.pitch if ctab else 0)
 
     # -- enqueue / finalise ---------------------------------------------------------------------
+    def _init_job(self, slot: "_Slot"):
+        """Static part of the slot's spp_batch_job (graph, workspace, tables, fan-outs)."""
+        cfg, sz, j = self._config, self._sz, slot.cjob
+        ctypes.memset(ctypes.byref(j), 0, ctypes.sizeof(j))
+        j.graph = self._g.c
+        j.ws = slot.ws.c
+        L = len(self._sizes)
+        j.n_hops = L
+        for h in range(L):
+            j.sizes[h] = self._sizes[h]
+            j.out_col_cap[h] = int(sz.hop_edges[h])
+        j.replace = 0
+        j.row_bytes = self._row_bytes
+        j.seeds_dev = slot.seeds.data_ptr()
+        j.meta_host = slot.meta_host.data_ptr()
+        j.stream = slot.stream.cuda_stream
+        if self._y is not None:
+            j.y_table = self._y.data_ptr()
+            j.y_row_bytes = self._y.size(-1) * self._y.element_size()
+        if not cfg.distributed:
+            if self._x_table is not None:
+                j.feature_mode = 1
+                j.table = self._x_table.ptr
+                j.table_pitch = self._x_table.pitch
+        else:
+            j.do_split = 1
+            j.use_cache = int(self._use_cache)
+            j.bucket_counts = slot.counts.data_ptr()
+            j.split_scratch = slot.split_scratch.data_ptr()
+            if self._fm is not None:
+                j.feature_mode = 2
+                j.fmap = self._fm
+            else:
+                j.fmap = self._split_fm
+
     def _enqueue(self):
         slot = self._free.popleft()
         start, stop = self._ranges[self._next]
@@ -721,84 +855,110 @@ class Session:
         rng_seed = (stop * 17 + 5) & 0xFFFFFFFF  # fast_sampler.cpp:994
         L = len(self._sizes)
         job = {"range": (start, stop), "bs": bs}
-        with torch.cuda.stream(slot.stream):
-            sp = slot.stream.cuda_stream
-            ws = slot.ws
-            if self._idx_host is not None:
-                seeds = slot.seeds[:bs]
-                if bs:
-                    seeds.copy_(self._idx_host[start:stop], non_blocking=True)
-            else:
-                seeds = self._idx[start:stop]
-            seeds_ptr = seeds.data_ptr()
-            arena = None
-            if self._full:
-                nb, adjs = _sample_stepwise(self._g, ws, seeds, self._sizes, False, rng_seed,
-                                            self._device)
+        ws = slot.ws
+        fdim, fdtype = self._feat_shape
+        if self._full:
+            # data-dependent sizes: stepwise ABI with host synchronisation (layer-wise inference)
+            with torch.cuda.stream(slot.stream):
+                sp = slot.stream.cuda_stream
+                if self._idx_host is not None:
+                    seeds = slot.seeds[:bs]
+                    if bs:
+                        slot.seeds_host[:bs].copy_(self._idx_host[start:stop])
+                        seeds.copy_(slot.seeds_host[:bs], non_blocking=True)
+                else:
+                    seeds = self._idx[start:stop]
+                nb, adjs = _sample_stepwise(self._g, ws, seeds, self._sizes, False, rng_seed, self._device)
                 job["ready"] = (nb, adjs)
-            else:
-                # one allocation for every structure output of the batch (rowptr / col per hop,
-                # and n_id / bucket ids / perm in distributed mode); exact-size views are cut in
+                n_dev = ws.meta_ptr(L)
+                if not cfg.distributed:
+                    x = torch.empty((nb if self._x_table is not None else 0, fdim), dtype=fdtype, device=self._device)
+                    if self._x_table is not None and nb:
+                        check(self._lib.spp_gather_rows_pitched(self._x_table.ptr, self._x_table.pitch, self._row_bytes,
+                                                                ws.n_ids.data_ptr(), 0, nb, None, x.data_ptr(), nb, sp),
+                              "spp_gather_rows_pitched")
+                    job["x"] = x
+                else:
+                    arena = torch.empty(3 * max(nb, 1), dtype=torch.int64, device=self._device)
+                    cap = max(nb, 1)
+                    check(self._lib.spp_sample_export_nids(ctypes.byref(ws.c), L, arena.data_ptr(), 1, cap, sp),
+                          "spp_sample_export_nids")
+                    job["n_id"], job["bucket_ids"], job["perm"] = arena[:cap], arena[cap:2 * cap], arena[2 * cap:]
+                    check(self._lib.spp_split_by_owner(ctypes.byref(self._split_fm), int(self._use_cache),
+                                                       ws.n_ids.data_ptr(), 0, nb, None, job["bucket_ids"].data_ptr(),
+                                                       job["perm"].data_ptr(), slot.counts.data_ptr(),
+                                                       slot.split_scratch.data_ptr(), sp), "spp_split_by_owner")
+                    if self._fm is not None:
+                        x = torch.empty((nb, fdim), dtype=fdtype, device=self._device)
+                        if nb:
+                            check(self._lib.spp_gather_partitioned(ctypes.byref(self._fm), self._row_bytes,
+                                                                   ws.n_ids.data_ptr(), 0, nb, None, x.data_ptr(), nb,
+                                                                   None, sp), "spp_gather_partitioned")
+                        job["x"] = x
+                    slot.meta_host[SPP_META_WORDS:].copy_(slot.counts, non_blocking=True)
+                job["y"] = self._labels_for(seeds, bs, sp)
+                slot.event.record(slot.stream)
+            slot.ticket = None
+        else:
+            j = slot.cjob
+            with torch.cuda.stream(slot.stream):  # the outputs belong to the slot's stream
+                # one allocation for every structure output of the batch (rowptr / col per hop, and
+                # n_id / bucket ids / perm in distributed mode); exact-size views are cut in
                 # _finalize once the meta block has arrived
                 arena = torch.empty(self._arena_words, dtype=torch.int64, device=self._device)
-                base = arena.data_ptr()
-                for h, (ro, co) in enumerate(self._arena_off):
-                    slot.c_rp[h] = base + 8 * ro
-                    slot.c_cp[h] = base + 8 * co
-                nid_ptr = base + 8 * self._arena_nid if cfg.distributed else None
-                check(self._lib.spp_sample_minibatch(ctypes.byref(self._g.c), seeds_ptr, bs, self._c_sizes, L, 0,
-                                                     ctypes.c_uint64(rng_seed), ctypes.byref(ws.c), slot.c_rp,
-                                                     slot.c_cp, self._c_caps, nid_ptr, sp), "spp_sample_minibatch")
-                job["arena"] = arena
-            n_dev = ws.meta_ptr(L)
-            fdim, fdtype = self._feat_shape
-            row_bytes = self._row_bytes
-            if not cfg.distributed:
-                if self._x_table is not None:
+                x = None
+                if j.feature_mode:
                     x = torch.empty((ws.max_nodes, fdim), dtype=fdtype, device=self._device)
-                    check(self._lib.spp_gather_rows(self._x_table.data_ptr(), row_bytes, ws.n_ids.data_ptr(), 0,
-                                                    ws.max_nodes, n_dev, x.data_ptr(), ws.max_nodes, sp),
-                          "spp_gather_rows")
-                else:
-                    x = torch.empty((0, fdim), dtype=fdtype, device=self._device)
+                y = None
+                if self._y is not None:
+                    y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
+            base = arena.data_ptr()
+            for h, (ro, co) in enumerate(self._arena_off):
+                j.out_rowptr[h] = base + 8 * ro
+                j.out_col[h] = base + 8 * co
+            if self._idx_host is not None:
+                if bs:
+                    slot.seeds_host[:bs].copy_(self._idx_host[start:stop])
+                j.seeds_host = slot.seeds_host.data_ptr() if bs else None
+                j.seeds_dev = slot.seeds.data_ptr()
+            else:
+                j.seeds_host = None
+                j.seeds_dev = self._idx.data_ptr() + 8 * start
+            j.batch_size = bs
+            j.rng_seed = rng_seed
+            j.x_out = x.data_ptr() if x is not None else None
+            j.y_out = y.data_ptr() if (y is not None and bs) else None
+            if cfg.distributed:
+                o, m = self._arena_nid, ws.max_nodes
+                j.n_id_out = base + 8 * o
+                j.bucket_ids = base + 8 * (o + m)
+                j.perm = base + 8 * (o + 2 * m)
+                job["n_id"], job["bucket_ids"], job["perm"] = arena[o:o + m], arena[o + m:o + 2 * m], arena[o + 2 * m:o + 3 * m]
+            job["arena"], job["y"] = arena, y
+            if x is not None:
                 job["x"] = x
+            elif not cfg.distributed:
+                job["x"] = torch.empty((0, fdim), dtype=fdtype, device=self._device)
+            if self._executor is not None:
+                t = self._lib.spp_executor_submit(self._executor, ctypes.byref(j))
+                if not t:
+                    raise SalientB200Error("spp_executor_submit failed: " + self._lib.spp_last_error().decode())
+                slot.ticket = t
             else:
-                if self._full:
-                    arena = torch.empty(3 * ws.max_nodes, dtype=torch.int64, device=self._device)
-                    n_id = arena[:ws.max_nodes]
-                    check(self._lib.spp_sample_export_nids(ctypes.byref(ws.c), L, n_id.data_ptr(), 1, ws.max_nodes, sp),
-                          "spp_sample_export_nids")
-                    o = 0
-                else:
-                    o = self._arena_nid
-                    n_id = arena[o:o + ws.max_nodes]
-                job["n_id"] = n_id
-                bucket_ids = arena[o + ws.max_nodes:o + 2 * ws.max_nodes]
-                perm = arena[o + 2 * ws.max_nodes:o + 3 * ws.max_nodes]
-                check(self._lib.spp_split_by_owner(ctypes.byref(self._split_fm), int(self._use_cache),
-                                                   ws.n_ids.data_ptr(), 0, ws.max_nodes, n_dev, bucket_ids.data_ptr(),
-                                                   perm.data_ptr(), slot.counts.data_ptr(),
-                                                   slot.split_scratch.data_ptr(), sp), "spp_split_by_owner")
-                job["bucket_ids"], job["perm"] = bucket_ids, perm
-                if self._fm is not None:
-                    x = torch.empty((ws.max_nodes, fdim), dtype=fdtype, device=self._device)
-                    check(self._lib.spp_gather_partitioned(ctypes.byref(self._fm), row_bytes, ws.n_ids.data_ptr(), 0,
-                                                           ws.max_nodes, n_dev, x.data_ptr(), ws.max_nodes, None, sp),
-                          "spp_gather_partitioned")
-                    job["x"] = x
-                slot.meta_host[SPP_META_WORDS:].copy_(slot.counts, non_blocking=True)
-            if self._y is not None and bs > 0:
-                y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
-                check(self._lib.spp_gather_rows(self._y.data_ptr(), self._y.size(-1) * self._y.element_size(),
-                                                seeds_ptr, 1, bs, None, y.data_ptr(), bs, sp), "spp_gather_rows(y)")
-                job["y"] = y
-            else:
-                job["y"] = None if self._y is None else torch.empty((0, self._y.size(-1)), dtype=self._y.dtype,
-                                                                     device=self._device)
-            slot.meta_host[:SPP_META_WORDS].copy_(ws.meta, non_blocking=True)
-            slot.event.record(slot.stream)
+                check(self._lib.spp_batch_enqueue(ctypes.byref(j)), "spp_batch_enqueue")
+                slot.event.record(slot.stream)
+                slot.ticket = None
         slot.job = job
         self._pending.append(slot)
+
+    def _labels_for(self, seeds: torch.Tensor, bs: int, sp: int):
+        if self._y is None:
+            return None
+        y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
+        if bs:
+            check(self._lib.spp_gather_rows(self._y.data_ptr(), self._y.size(-1) * self._y.element_size(),
+                                            seeds.data_ptr(), 1, bs, None, y.data_ptr(), bs, sp), "spp_gather_rows(y)")
+        return y
 
     def _finalize(self, slot: _Slot):
         job = slot.job
@@ -821,7 +981,7 @@ class Session:
         start, stop = job["range"]
         if not cfg.distributed:
             x = job["x"]
-            out = (x[:nb] if x.size(0) >= nb else x, job["y"], adjs, (start, stop))
+            out = (x[:nb] if x.size(0) > nb else x, job["y"], adjs, (start, stop))
         else:
             counts = slot.meta_host[SPP_META_WORDS:].tolist()
             P = self._P
@@ -863,6 +1023,8 @@ class Session:
             return
         self._released = True
         for s in self._pending:  # abandoned in-flight work (Session dropped early)
+            if s.ticket is not None:
+                self._lib.spp_executor_wait(self._executor, s.ticket)
             s.stream.synchronize()
             s.job = None
         self._pending.clear()
@@ -890,15 +1052,29 @@ class Session:
     def config(self) -> Config:
         return self._config
 
+    def _slot_done(self, slot: "_Slot") -> bool:
+        if slot.ticket is None:
+            return slot.event.query()
+        r = self._lib.spp_executor_poll(self._executor, slot.ticket)
+        if r < 0:
+            check(r, "spp_executor_poll")
+        return r == 1
+
+    def _slot_wait(self, slot: "_Slot") -> None:
+        if slot.ticket is None:
+            slot.event.synchronize()
+        else:
+            check(self._lib.spp_executor_wait(self._executor, slot.ticket), "spp_executor_wait")
+
     def _get(self, blocking: bool):
         if self._num_consumed == self._num_total:
             return None
         slot = self._pending[0]
-        if not slot.event.query():
+        if not self._slot_done(slot):
             if not blocking:
                 return None
             t0 = time.perf_counter()
-            slot.event.synchronize()
+            self._slot_wait(slot)
             self.total_blocked_dur += datetime.timedelta(microseconds=int((time.perf_counter() - t0) * 1e6))
             self.total_blocked_occasions += 1
         self._pending.popleft()
@@ -927,7 +1103,7 @@ class Session:
     num_consumed_batches = property(lambda self: self._num_consumed)
     num_total_batches = property(lambda self: self._num_total)
     approx_num_complete_batches = property(lambda self: self._num_consumed + sum(
-        1 for s in self._pending if s.event.query()))
+        1 for s in self._pending if self._slot_done(s)))
 
     # -- async_slice_tensors (fast_sampler.cpp:720-775): serve other ranks' requests for rows that
     #    the reference keeps on the host; here those rows are in HBM too -----------------------

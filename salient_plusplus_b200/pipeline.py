@@ -34,9 +34,13 @@ class MiniBatchPipeline:
         self.L = len(self.sizes)
         self.bs = int(batch_size)
         self.sz = _sampler_sizes(self.bs, self.sizes, self.g)
+        # x_table: a fast_sampler._FeatureTable (possibly row-padded) or a dense tensor
+        if x_table is not None and isinstance(x_table, torch.Tensor):
+            from .fast_sampler import feature_table
+            x_table = feature_table(x_table)
         self.x_table, self.y_table, self.fm = x_table, y_table, feature_map
         if x_table is not None:
-            feat_dim, feat_dtype = x_table.size(1), x_table.dtype
+            feat_dim, feat_dtype = x_table.dim, x_table.dtype
         self.feat_dim, self.feat_dtype = feat_dim, feat_dtype
         self.row_bytes = feat_dim * torch.empty(0, dtype=feat_dtype).element_size()
         self.split, self.use_cache = split, use_cache
@@ -80,9 +84,9 @@ class MiniBatchPipeline:
                                                   s.ws.max_nodes, n_dev, s.x.data_ptr(), s.ws.max_nodes, None,
                                                   s.stream.cuda_stream), "spp_gather_partitioned")
         elif self.x_table is not None:
-            check(self.lib.spp_gather_rows(self.x_table.data_ptr(), self.row_bytes, s.ws.n_ids.data_ptr(), 0,
-                                           s.ws.max_nodes, n_dev, s.x.data_ptr(), s.ws.max_nodes,
-                                           s.stream.cuda_stream), "spp_gather_rows")
+            check(self.lib.spp_gather_rows_pitched(self.x_table.ptr, self.x_table.pitch, self.row_bytes,
+                                                   s.ws.n_ids.data_ptr(), 0, s.ws.max_nodes, n_dev, s.x.data_ptr(),
+                                                   s.ws.max_nodes, s.stream.cuda_stream), "spp_gather_rows_pitched")
 
     def labels(self, s: _PipeSlot, seeds_ptr: int, bs: int):
         if self.y_table is not None and bs > 0:

@@ -148,6 +148,7 @@ class FastSamplerConfig:
     # extensions (see fast_sampler.Config)
     partition_tables: Optional[list] = None
     peer_table_ptrs: Optional[list] = None
+    peer_table_pitch: int = 0
     fused_gather: bool = True
 
     def to_fast_sampler(self) -> fast_sampler.Config:

@@ -35,7 +35,7 @@ def test_exports_match_header(lib):
 
 def test_struct_layouts_match_header():
     from salient_plusplus_b200 import _lib
-    assert ctypes.sizeof(_lib.FeatureMap) == 4 + 4 + 17 * 8 + 16 * 8 + 8 + 8
+    assert ctypes.sizeof(_lib.FeatureMap) == 4 + 4 + 17 * 8 + 16 * 8 + 8 + 8 + 16
     assert ctypes.sizeof(_lib.Graph) == 32
     assert ctypes.sizeof(_lib.SamplerWs) == 96
     assert ctypes.sizeof(_lib.SamplerSizes) == 5 * 8 + 2 * 8 * 8

@@ -352,3 +352,28 @@ def test_gather_partitioned_equals_global_gather(fs, P, rank, use_cache, dim, dt
         assert c[1] == int(torch.isin(n_id, cv).sum())
     else:
         assert c[1] == 0
+
+
+@pytest.mark.parametrize("dim,dtype,pitch_elems", [(100, torch.float16, 128), (50, torch.float32, 64), (7, torch.uint8, 16)])
+def test_gather_rows_pitched(fs, dim, dtype, pitch_elems):
+    """Source rows `pitch` bytes apart (the padded resident layout), dense output."""
+    from salient_plusplus_b200 import _lib
+    L = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    n = 3000
+    dense = (torch.randn((n, dim), generator=g) * 50).to(dtype)
+    padded = torch.full((n, pitch_elems), 77, dtype=dtype)
+    padded[:, :dim] = dense
+    idx = torch.randint(0, n, (5001,), generator=g)
+    pd, ix = padded.cuda(), idx.cuda()
+    out = torch.empty((idx.numel(), dim), dtype=dtype, device="cuda")
+    es = dense.element_size()
+    _lib.check(L.spp_gather_rows_pitched(pd.data_ptr(), pitch_elems * es, dim * es, ix.data_ptr(), 1, ix.numel(), None,
+                                         out.data_ptr(), ix.numel(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), dense[idx])
+    t = fs.feature_table(dense)
+    assert t.row_bytes == dim * es and t.pitch % es == 0 and t.pitch >= t.row_bytes
+    if dim * es == 200:
+        assert t.pitch == 256
+        assert torch.equal(t.storage[:, :dim].cpu(), dense)

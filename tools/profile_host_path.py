@@ -1,7 +1,5 @@
-"""cProfile of the public-API path (FastSampler -> DevicePrefetcher) to find host overheads."""
-import cProfile
+"""Per-batch latency distribution of the public-API path (FastSampler -> DevicePrefetcher)."""
 import os
-import pstats
 import sys
 import time
 
@@ -27,17 +25,22 @@ def run(k):
     cfg = FastSamplerConfig(x_cpu=x, x_gpu=torch.empty((0, f), dtype=dt), y=y, rowptr=rowptr, col=col,
                             idx=idx[:k * bs], batch_size=bs, sizes=[15, 10, 5], skip_nonfull_batch=False,
                             pin_memory=True, distributed=False)
+    t0 = time.perf_counter()
     it = DevicePrefetcher([dev], iter(FastSampler(16, 8, cfg)))
-    c = 0
+    t_init = time.perf_counter() - t0
+    lat = []
+    t = time.perf_counter()
     for (b,) in it:
-        c += b.x.size(0)
+        t2 = time.perf_counter()
+        lat.append(t2 - t)
+        t = t2
     torch.cuda.synchronize()
-    return c
+    return t_init, lat, time.perf_counter() - t0
 
 
 run(20)
-t = time.perf_counter(); run(K); dt_ = time.perf_counter() - t
-print(f"{K / dt_:.1f} batches/s ({dt_ / K * 1e6:.0f} us/batch)")
-pr = cProfile.Profile()
-pr.enable(); run(K); pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+for rep in range(6):
+    t_init, lat, tot = run(K)
+    lat.sort()
+    print(f"rep {rep}: {K / tot:7.1f} batches/s  init {t_init * 1e3:6.2f} ms  per-batch us: p10 {lat[20] * 1e6:6.0f} "
+          f"p50 {lat[100] * 1e6:6.0f} p90 {lat[180] * 1e6:6.0f} max {lat[-1] * 1e6:7.0f}", flush=True)
