@@ -278,6 +278,8 @@ uint64_t spp_executor_submit(void* executor, const spp_batch_job* job);
 int spp_executor_poll(void* executor, uint64_t ticket);
 /* blocks until the job's GPU work has completed; 0 or an error code */
 int spp_executor_wait(void* executor, uint64_t ticket);
+/* diagnostics: steady-clock seconds at which the job was submitted, started and finished issuing */
+int spp_executor_times(void* executor, uint64_t ticket, double* out3_host);
 
 /* ------------------------------------------------------------------------------------------
  * Peer mapping (CUDA IPC) for the P2P gather.  Host-synchronous.

@@ -32,7 +32,7 @@ EXPORTED = [
     "spp_sampler_sizes", "spp_sample_minibatch", "spp_sample_begin", "spp_sample_hop_count",
     "spp_sample_hop_fill", "spp_sample_export_nids",
     "spp_batch_enqueue", "spp_executor_create", "spp_executor_destroy", "spp_executor_submit",
-    "spp_executor_poll", "spp_executor_wait",
+    "spp_executor_poll", "spp_executor_wait", "spp_executor_times",
     "spp_ipc_export", "spp_ipc_import", "spp_ipc_close", "spp_enable_peer_access",
 ]
 
@@ -137,6 +137,7 @@ def load() -> ctypes.CDLL:
     L.spp_executor_submit.argtypes = [vp, POINTER(BatchJob)]
     L.spp_executor_poll.argtypes = [vp, c_uint64]
     L.spp_executor_wait.argtypes = [vp, c_uint64]
+    L.spp_executor_times.argtypes = [vp, c_uint64, POINTER(ctypes.c_double)]
     L.spp_ipc_export.argtypes = [vp, POINTER(c_uint8), POINTER(i64)]
     L.spp_ipc_import.argtypes = [POINTER(c_uint8), i64, POINTER(vp)]
     L.spp_ipc_close.argtypes = [vp, i64]

@@ -6,6 +6,7 @@
 // and records a completion event, so the (Python) consumer thread only allocates outputs, posts a
 // job descriptor and later waits on the ticket.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -58,6 +59,10 @@ extern "C" int spp_batch_enqueue(const spp_batch_job* j) {
 
 namespace spp {
 
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 constexpr int kRing = 256;  // tickets in flight (a Session keeps <= 8)
 
 struct Executor {
@@ -70,6 +75,7 @@ struct Executor {
   uint64_t next_ticket = 1;
   uint64_t issued = 0;  // every ticket <= issued has had its CUDA calls issued
   cudaEvent_t events[kRing];
+  double t_submit[kRing], t_begin[kRing], t_end[kRing];  // steady-clock seconds (diagnostics)
   int status[kRing];
   std::string errors[kRing];
 
@@ -94,10 +100,12 @@ struct Executor {
         queue.pop_front();
       }
       const int slot = (int)(item.first % kRing);
+      t_begin[slot] = now_s();
       int rc = spp_batch_enqueue(&item.second);
       std::string err;
       if (rc != 0) err = spp_last_error();
       cudaError_t e = cudaEventRecord(events[slot], (cudaStream_t)item.second.stream);
+      t_end[slot] = now_s();
       if (rc == 0 && e != cudaSuccess) {
         rc = (int)e;
         err = cudaGetErrorString(e);
@@ -168,6 +176,7 @@ uint64_t spp_executor_submit(void* executor, const spp_batch_job* job) {
       return 0;
     }
     t = ex->next_ticket++;
+    ex->t_submit[t % spp::kRing] = spp::now_s();
     ex->queue.emplace_back(t, *job);
   }
   ex->cv_work.notify_one();
@@ -188,6 +197,18 @@ int spp_executor_poll(void* executor, uint64_t ticket) {
   }
   int rc = spp::cuda_fail(e, "cudaEventQuery");
   return rc > 0 ? -rc : rc;
+}
+
+/* diagnostics: steady-clock seconds at which `ticket` was submitted / started / finished issuing */
+int spp_executor_times(void* executor, uint64_t ticket, double* out3) {
+  auto* ex = static_cast<spp::Executor*>(executor);
+  if (!ex || !out3) return spp::fail(SPP_EINVAL, "spp_executor_times: null argument");
+  std::lock_guard<std::mutex> lk(ex->mu);
+  const int slot = (int)(ticket % spp::kRing);
+  out3[0] = ex->t_submit[slot];
+  out3[1] = ex->t_begin[slot];
+  out3[2] = ex->t_end[slot];
+  return 0;
 }
 
 int spp_executor_wait(void* executor, uint64_t ticket) {

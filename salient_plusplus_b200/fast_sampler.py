@@ -705,6 +705,7 @@ class Session:
         if not self._full:
             for s_ in self._slots:
                 self._init_job(s_)
+                self._prime_allocator(s_)
         self._free = deque(self._slots)
         self._pending: deque = deque()
         self._freq = None
@@ -845,6 +846,28 @@ class Session:
                 j.fmap = self._fm
             else:
                 j.fmap = self._split_fm
+
+    def _prime_allocator(self, slot: "_Slot", blocks: int = 3):
+        """Per-batch outputs are allocated at their upper bounds from PyTorch's caching allocator
+        on the slot's stream.  A cache miss there is a cudaMalloc of a few hundred MB (2-30 ms,
+        measured), so the first time a slot sees a given output size its pool is primed with the
+        blocks a steady-state pipeline needs (in flight + held by the consumer + prefetched)."""
+        fdim, fdtype = self._feat_shape
+        x_rows = slot.ws.max_nodes if slot.cjob.feature_mode else 0
+        key = (self._arena_words, x_rows, fdim, fdtype)
+        primed = getattr(slot, "primed", None)
+        if primed is None:
+            primed = slot.primed = set()
+        if key in primed:
+            return
+        primed.add(key)
+        with torch.cuda.stream(slot.stream):
+            keep = []
+            for _ in range(blocks):
+                keep.append(torch.empty(self._arena_words, dtype=torch.int64, device=self._device))
+                if x_rows:
+                    keep.append(torch.empty((x_rows, fdim), dtype=fdtype, device=self._device))
+            del keep
 
     def _enqueue(self):
         slot = self._free.popleft()
@@ -1075,6 +1098,13 @@ class Session:
                 return None
             t0 = time.perf_counter()
             self._slot_wait(slot)
+            if os.environ.get("SPP_DEBUG_TIMING") and slot.ticket is not None and self._num_consumed < 2:
+                tt = (ctypes.c_double * 3)()
+                self._lib.spp_executor_times(self._executor, slot.ticket, tt)
+                now = time.clock_gettime(time.CLOCK_MONOTONIC)
+                print("[spp] batch %d: queued %.0f us, issuing %.0f us, issue->complete %.0f us (waited %.0f us)" % (
+                    self._num_consumed, (tt[1] - tt[0]) * 1e6, (tt[2] - tt[1]) * 1e6, (now - tt[2]) * 1e6,
+                    (time.perf_counter() - t0) * 1e6), flush=True)
             self.total_blocked_dur += datetime.timedelta(microseconds=int((time.perf_counter() - t0) * 1e6))
             self.total_blocked_occasions += 1
         self._pending.popleft()
