@@ -1,0 +1,70 @@
+"""Host-side logic that needs neither a GPU nor the reference: batch ranges, config mirror,
+feature-map marshalling, Adj wrappers."""
+import ctypes
+
+import pytest
+import torch
+
+from oracle import oracle as O
+from salient_plusplus_b200 import _lib
+from salient_plusplus_b200.adj import Adj, Adj__from_fast_sampler
+from salient_plusplus_b200.fast_sampler import Cache, Config, RangePartitionBook, _batch_ranges, make_feature_map
+from salient_plusplus_b200.samplers import FastSamplerConfig, PreparedBatch, ProtoDistributedBatch
+
+
+@pytest.mark.parametrize("n,bs,skip,exact,B", [(1000, 64, False, False, 0), (1000, 64, True, False, 0), (1024, 64, True, False, 0),
+                                              (1000, 64, False, True, 7), (10, 64, False, True, 3), (0, 64, False, False, 0),
+                                              (63, 64, True, False, 0), (100, 1, False, True, 100)])
+def test_batch_ranges_match_oracle(n, bs, skip, exact, B):
+    cfg = Config()
+    cfg.batch_size, cfg.skip_nonfull_batch, cfg.force_exact_num_batches, cfg.exact_num_batches = bs, skip, exact, B
+    assert _batch_ranges(n, cfg) == O.batch_ranges(n, bs, skip, exact, B)
+
+
+def test_fast_sampler_config_mirror():
+    t = torch.zeros(4, 2)
+    cfg = FastSamplerConfig(x_cpu=t, x_gpu=t, y=None, rowptr=torch.zeros(5, dtype=torch.int64), col=torch.zeros(0, dtype=torch.int64),
+                            idx=torch.arange(130), batch_size=64, sizes=[15, 10, 5], skip_nonfull_batch=False,
+                            pin_memory=True, distributed=False)
+    assert cfg.get_num_batches() == 3
+    cfg.skip_nonfull_batch = True
+    assert cfg.get_num_batches() == 2
+    cfg.force_exact_num_batches, cfg.exact_num_batches = True, 9
+    assert cfg.get_num_batches() == 9
+    c = cfg.to_fast_sampler()
+    assert c.sizes == [15, 10, 5] and c.batch_size == 64 and isinstance(c.cache, Cache) and c.partition_book is None
+    cfg.distributed = True
+    cfg.partition_book = RangePartitionBook(1, 2, torch.tensor([0, 2, 4]))
+    assert cfg.to_fast_sampler().partition_book.rank == 1
+
+
+def test_feature_map_marshalling():
+    fm = make_feature_map([0, 10, 25, 40], 1, [None, None, None], None, None, [111, 0, 333], 256, 128)
+    assert fm.num_parts == 3 and fm.rank == 1 and list(fm.offsets)[:5] == [0, 10, 25, 40, 40]
+    assert fm.tables[0] == 111 and fm.tables[1] is None and fm.tables[2] == 333
+    assert fm.cache_table is None and fm.cache_map is None and fm.table_pitch == 256 and fm.cache_pitch == 128
+    with pytest.raises(RuntimeError):
+        RangePartitionBook(0, 1, torch.arange(40))._off()      # more than SPP_MAX_PARTS partitions
+
+
+def test_adj_and_batches():
+    rowptr, col = torch.tensor([0, 1, 3]), torch.tensor([2, 0, 1])
+    a = Adj__from_fast_sampler((rowptr, col, torch.empty(0, dtype=torch.int64), (2, 3)))
+    assert isinstance(a, Adj) and a.size == (3, 2) and a.adj_t.sparse_sizes() == (2, 3)
+    pb = PreparedBatch.from_fast_sampler((torch.zeros(3, 4), torch.zeros(2, 1), [(rowptr, col, torch.empty(0), (2, 3))], (5, 7)))
+    assert pb.batch_size == 2 and pb.num_total_nodes == 3 and pb.y.shape == (2,) and pb.idx_range == slice(5, 7)
+
+    class B:
+        partition_nids = [torch.tensor([1]), torch.tensor([2, 3])]
+        sliced_cpu_features = torch.zeros(0, 4)
+        sliced_cpu_labels = torch.zeros(2, 1)
+        cached_nids = torch.zeros(0, dtype=torch.int64)
+        perm_partition_to_mfg = torch.tensor([0, 1, 2])
+        adjs = [(rowptr, col, torch.empty(0), (2, 3))]
+        idx_range = (0, 2)
+    p = ProtoDistributedBatch.from_fast_sampler(B())
+    assert p.num_total_nodes == 3 and p.num_cached_nodes == 0 and p.idx_range == slice(0, 2) and p.x is None
+
+
+def test_struct_sizes_stable():
+    assert ctypes.sizeof(_lib.BatchJob) == 824
