@@ -42,7 +42,8 @@ WORKLOADS = {
               "ogbn-arxiv-shaped synthetic (169K nodes, 1.17M directed edges symmetrised, 128-d fp32), "
               "fanout (15,10,5), batch 1024"),
     "papers100M": ("papers100M", [15, 10, 5], 1024,
-                   "ogbn-papers100M-shaped synthetic (111M nodes, 1.6B directed edges, 128-d fp16), fanout (15,10,5)"),
+                   "ogbn-papers100M-shaped synthetic (111M nodes, 1.6B CSR entries = 0.8B directed edges symmetrised, "
+                   "128-d fp16), fanout (15,10,5), batch 1024"),
 }
 METRIC = "sampled_and_gathered_minibatches_per_sec"
 UNIT = "batches/s"
@@ -66,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -124,6 +125,8 @@ def dist_env():
 def make_graph(shape: str, scale: float, device):
     from salient_plusplus_b200 import synthetic as S
     n, e, f, dt = S.SHAPES[shape]
+    if shape == "papers100M":
+        e //= 2  # BASELINE's 1.6B is taken as the CSR entry count ("say which")
     n, e = max(1024, int(n * scale)), max(4096, int(e * scale))
     rowptr, col = S.powerlaw_graph(n, e, seed=1, device=device)
     return n, f, dt, rowptr, col
@@ -263,7 +266,11 @@ def ours(args):
     y = S.labels(n, seed=3, device=dev)
     row_bytes = f * x_full.element_size()
 
-    P = world
+    P = max(world, args.parts)
+    if P % world != 0:
+        raise SystemExit("--parts must be a multiple of the number of GPUs")
+    if P > world and world > 1:
+        raise SystemExit("more partitions than GPUs is only emulated on a single GPU")
     off = S.equal_partition_offsets(n, P)
     lo, hi = int(off[rank]), int(off[rank + 1])
     need = (W + K) * bs
@@ -276,20 +283,28 @@ def ours(args):
     cache = fs.Cache()
     x_local = x_full
     cache_rows = 0
+    part_tensors = None
     if P > 1:
         x_local = x_full[lo:hi].clone()
         cache_rows = int((n / P) * args.cache_pct / 100.0)
         cv = S.degree_cache_vertices(rowptr, off.to(dev), rank, cache_rows)
         cache = fs.Cache(rank, P, cv, x_full[cv].contiguous())
-        del x_full
-        torch.cuda.empty_cache()
-        from salient_plusplus_b200 import peer
         ltab = fs.feature_table(x_local)      # resident copy, 128-byte-multiple row pitch
         ctab = cache.device_table()
-        ptrs = peer.exchange_partition_tables(ltab.storage, rank, P)
-        ptrs[rank] = 0
         tables = [None] * P
         tables[rank] = ltab.storage
+        if world > 1:
+            del x_full
+            torch.cuda.empty_cache()
+            from salient_plusplus_b200 import peer
+            ptrs = peer.exchange_partition_tables(ltab.storage, rank, P)
+            ptrs[rank] = 0
+        else:  # every partition lives on this GPU (single-GPU point of a partitioned config)
+            part_tensors = [x_full[int(off[p]):int(off[p + 1])] if p != rank else None for p in range(P)]
+            ptrs = [0] * P
+            for p in range(P):
+                if p != rank:
+                    tables[p] = fs.feature_table(part_tensors[p]).storage
         fm = fs.make_feature_map(off.tolist(), rank, tables, ctab.storage, cache.device_map(n), ptrs, ltab.pitch,
                                  ctab.pitch)
 
@@ -318,10 +333,10 @@ def ours(args):
         torch.cuda.synchronize()
 
     # ---- value: device-timed, inputs resident in HBM -------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()  # sampled from here to the end of the end-to-end loop (both timed regions)
     run_batches(0, W)
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
     launches0 = lib.spp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
@@ -334,7 +349,6 @@ def ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(lib.spp_launch_count() - launches0)
-    clk = clocks.stop()
 
     # ---- roofline pass: the feature gather timed with CUDA events on its own stream -----------
     evs = run_batches(W, min(K, 64), time_gather=True, single_stream=True)
@@ -351,6 +365,13 @@ def ours(args):
     alg_bytes_per_launch = mean_nodes * (2 * row_bytes + idx_bytes)
     g_ms_avg = g_ms / max(1, len(evs))
     peak, peak_src = measured_peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_gather_traffic.json")
+    if args.workload == "products" and P == 1 and os.path.exists(tp):
+        try:
+            traffic = int(json.load(open(tp))["traffic_bytes_per_launch"])  # ncu --set full, dram rd + wr
+        except Exception:  # noqa: BLE001
+            traffic = None
     achieved = alg_bytes_per_launch / (g_ms_avg * 1e-3) / 1e9 if g_ms_avg > 0 else 0.0
 
     # ---- e2e: public API, seeds in pinned host memory, per-step H2D + D2H ---------------------
@@ -362,9 +383,11 @@ def ours(args):
             sizes=list(sizes), skip_nonfull_batch=False, pin_memory=True, distributed=P > 1,
             partition_book=fs.RangePartitionBook(rank, P, off) if P > 1 else None, cache=cache,
             force_exact_num_batches=False, exact_num_batches=0, count_remote_frequency=False, use_cache=P > 1)
-        if P > 1:
+        if P > 1 and world > 1:
             cfg.peer_table_ptrs = ptrs
             cfg.peer_table_pitch = ltab.pitch
+        elif P > 1:
+            cfg.partition_tables = part_tensors
         ta = time.perf_counter()
         sampler = FastSampler(16, max(args.depth, 4), cfg)
         it = iter(sampler)
@@ -399,6 +422,7 @@ def ours(args):
         tl = tn
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    clk = clocks.stop()
     first_us = lat[0] * 1e6
     top3 = sorted(range(len(lat)), key=lambda i: -lat[i])[:3]
     top3 = [(i, round(lat[i] * 1e6)) for i in top3]
@@ -436,7 +460,7 @@ def ours(args):
                                            f"degree-ranked cache, P2P gather over NVLink" if P > 1 else ""),
                        "graph_generator": "Chung-Lu power law gamma=2.5 head_offset=100 seed=1, symmetrised, deduplicated",
                        "nnz": int(col.numel()), "mean_nodes_per_batch": round(mean_nodes, 1),
-                       "streams_in_flight": D, "scale": args.scale,
+                       "streams_in_flight": D, "scale": args.scale, "feature_partitions": P,
                        "l2": "inputs larger than L2 (feature table + CSR >> 126 MB, random rows)"},
             "gathered_GBps": round(value * mean_nodes * row_bytes / 1e9, 2),
             "e2e": {"value": round(e2e_v, 2), "unit": UNIT, "h2d_bytes_per_step": bs * 8,
@@ -448,7 +472,7 @@ def ours(args):
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_gather (feature gather)", "achieved": round(achieved, 1),
-                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "avg_launch_ms": round(g_ms_avg, 5),
                          "algorithmic_bytes_per_launch": int(alg_bytes_per_launch),
                          "bytes_model": "N_b * (2*row_bytes + 4)", "launches_timed": len(evs)},
@@ -471,6 +495,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (testing only)")
     ap.add_argument("--depth", type=int, default=4, help="mini-batches in flight (CUDA streams)")
     ap.add_argument("--cache-pct", type=float, default=15.0)
+    ap.add_argument("--parts", type=int, default=0, help="feature partitions (default: one per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile the public-API loop (stderr)")
     args = ap.parse_args()
