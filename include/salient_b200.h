@@ -282,6 +282,18 @@ int spp_executor_wait(void* executor, uint64_t ticket);
 int spp_executor_times(void* executor, uint64_t ticket, double* out3_host);
 
 /* ------------------------------------------------------------------------------------------
+ * VIP (vertex inclusion probability) propagation -- set-up time, decides the replicated cache
+ * (driver/drivers/ddp.py:134-239, caching/vip.py:123-180).  One hop, fp64:
+ *   t(u)     = min(1, fanout/deg(u)) * p_in[u]
+ *   p_out[v] = 1 - exp(-sum_{u in N(v)} t(u))              exact == 0  (driver, ddp.py:219-224)
+ *            = 1 - exp( sum_{u in N(v)} log(1 - t(u)))     exact != 0  (caching/vip.py:166-172)
+ *   not_total[v] *= 1 - p_out[v]   (if not_total != NULL)
+ * scratch: double[num_nodes].  p_in and p_out must not alias.
+ * ---------------------------------------------------------------------------------------- */
+int spp_vip_hop(const spp_graph* graph_host, double fanout, int exact, const double* p_in,
+                double* p_out, double* not_total, double* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Peer mapping (CUDA IPC) for the P2P gather.  Host-synchronous.
  *   export: handle_host receives 64 bytes, *offset_host the offset of `ptr` inside its
  *           allocation; import (in another process) returns a device pointer valid there.

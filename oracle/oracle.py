@@ -291,3 +291,51 @@ def distributed_binning(n_id, offsets, rank: int, world_size: int, x_gpu_rows: i
     perm[flipped] = np.arange(n_id.size, dtype=np.int64)                 # :1249-1252
     cached_nids = cache.nid2cachenid(cached)                             # :1256
     return partition_nids, cached_nids, perm, local_on_cpu
+
+
+# ---------------------------------------------------------------------------------------------
+# VIP analytic model, fp64 numpy restatement.
+#   exact=True : caching/vip.py:123-180 (vip_analytical, log-product form).  PINNED: the
+#                reference's own function was run here (torch_scatter.segment_csr replaced by a
+#                stand-in with its published semantics) -> tests/golden/vip.npz, checked in
+#                tests/test_oracle_golden.py at the reference's fp32 precision.
+#   exact=False: driver/drivers/ddp.py:134-239 (get_frequency_tensors_fast, first-order form the
+#                driver actually uses).  PARITY UNPINNED: that function needs a CUDA device, an
+#                initialised process group and torch_scatter; it differs from the pinned form only
+#                in the per-neighbour term (:219-224 vs vip.py:166-172).
+# ---------------------------------------------------------------------------------------------
+def vip_probabilities(rowptr, col, train_idx, batch_size: int, fanouts, exact: bool = False) -> np.ndarray:
+    rowptr, col = _i64(rowptr), _i64(col)
+    n = rowptr.size - 1
+    deg = (rowptr[1:] - rowptr[:-1]).astype(np.float64)            # ddp.py:153-154
+    p = np.zeros(n, dtype=np.float64)
+    p[_i64(train_idx)] = float(batch_size) / float(len(train_idx))  # :160
+    not_total = np.ones(n, dtype=np.float64)
+    nonempty = rowptr[1:] > rowptr[:-1]
+    for fanout in fanouts:                                          # :193
+        with np.errstate(divide="ignore"):
+            w = np.minimum(1.0, float(fanout) / deg)                # :221
+        t = w * p
+        if exact:                                                   # vip.py:166-172
+            with np.errstate(divide="ignore"):
+                t = -np.log(1.0 - t)
+        wp = t[col]
+        s = np.zeros(n, dtype=np.float64)
+        if col.size:
+            starts = np.minimum(rowptr[:-1], col.size - 1)
+            s = np.add.reduceat(wp, starts)                         # segment_csr(..., reduce='add') :222
+            s[~nonempty] = 0.0
+        p = 1.0 - np.exp(-s)                                        # :224
+        not_total *= (1.0 - p)                                      # :229-231
+    return 1.0 - not_total                                          # :233
+
+
+def select_cache_vertices(vip, offsets, rank: int, num_to_cache: int) -> np.ndarray:
+    """ddp.py:433-439 (with a stable sort) + owner-major bucketing :504-509,555."""
+    off = _i64(offsets)
+    score = np.array(vip, dtype=np.float64, copy=True)
+    score[off[rank]:off[rank + 1]] = 0.0
+    k = min(int(num_to_cache), int(np.count_nonzero(score)))
+    order = np.argsort(-score, kind="stable")[:k]
+    owner = nid2partid(off, order)
+    return np.concatenate([order[owner == p] for p in range(off.size - 1)]) if k else np.empty(0, dtype=np.int64)

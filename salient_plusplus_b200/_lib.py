@@ -33,6 +33,7 @@ EXPORTED = [
     "spp_sample_hop_fill", "spp_sample_export_nids",
     "spp_batch_enqueue", "spp_executor_create", "spp_executor_destroy", "spp_executor_submit",
     "spp_executor_poll", "spp_executor_wait", "spp_executor_times",
+    "spp_vip_hop",
     "spp_ipc_export", "spp_ipc_import", "spp_ipc_close", "spp_enable_peer_access",
 ]
 
@@ -138,6 +139,7 @@ def load() -> ctypes.CDLL:
     L.spp_executor_poll.argtypes = [vp, c_uint64]
     L.spp_executor_wait.argtypes = [vp, c_uint64]
     L.spp_executor_times.argtypes = [vp, c_uint64, POINTER(ctypes.c_double)]
+    L.spp_vip_hop.argtypes = [POINTER(Graph), ctypes.c_double, ci, vp, vp, vp, vp, vp]
     L.spp_ipc_export.argtypes = [vp, POINTER(c_uint8), POINTER(i64)]
     L.spp_ipc_import.argtypes = [POINTER(c_uint8), i64, POINTER(vp)]
     L.spp_ipc_close.argtypes = [vp, i64]

@@ -109,3 +109,31 @@ def test_products_full_size_split_roundtrip(data):
         assert torch.equal(b.x, x[n_id])
         assert b.cached_nids.numel() > 0 and b.partition_nids[rank].numel() > 0
     assert sess.blocking_get_batch_distributed() is None
+
+
+def test_products_full_size_layerwise_full_neighbourhood_bitexact(data):
+    """BASELINE config 3: one-hop full-neighbourhood batches (sizes=[-1], layer-wise inference,
+    driver/models.py:441-495) on the full-size products-shaped graph, bit-exact against the oracle
+    (= the reference algorithm), including a hub-heavy batch (the highest-degree nodes)."""
+    import numpy as np
+    from oracle import oracle as O
+    from salient_plusplus_b200 import fast_sampler as fs
+    dev, N, rowptr, col, x, y = data
+    rp_h, col_h = rowptr.cpu().numpy(), col.cpu().numpy()
+    deg = rowptr[1:] - rowptr[:-1]
+    hubs = torch.argsort(deg, descending=True)[:1024]
+    batches = [torch.arange(0, 1024, device=dev), torch.arange(N - 1024, N, device=dev), hubs]
+    cfg = fs.Config()
+    cfg.x_cpu, cfg.y, cfg.rowptr, cfg.col = x, y, rowptr, col
+    cfg.idx = torch.cat(batches)
+    cfg.batch_size, cfg.sizes = 1024, [-1]
+    sess = fs.Session(1, 2, cfg)
+    for seeds in batches:
+        xb, yb, adjs, (st, en) = sess.blocking_get_batch()
+        on, oa = O.multilayer_sample(seeds.cpu().numpy(), [-1], rp_h, col_h)
+        (rp, cl, e_id, size), (orp, ocl, _, osize) = adjs[0], oa[0]
+        assert tuple(size) == osize and e_id.numel() == 0
+        assert np.array_equal(rp.cpu().numpy(), orp) and np.array_equal(cl.cpu().numpy(), ocl)
+        assert torch.equal(xb, x[torch.from_numpy(on).to(dev)])
+        assert torch.equal(yb, y[seeds])
+    assert sess.blocking_get_batch() is None

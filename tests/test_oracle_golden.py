@@ -115,3 +115,33 @@ def test_mt19937_known_answer():
     for _ in range(10000):
         v = L.spo_mt_next(buf)
     assert v == 4123659995
+
+
+@pytest.mark.parametrize("fi", [0, 1])
+def test_vip_analytical_against_reference_module(fi):
+    """Golden vectors produced by the reference's own caching/vip.py:vip_analytical (fp32)."""
+    g = np.load(os.path.join(G, "vip.npz"))
+    fanouts = g[f"fanouts{fi}"].tolist()
+    for p in range(4):
+        got = O.vip_probabilities(g["rowptr"], g["col"], g[f"train{p}"], 32, fanouts, exact=True)
+        want = g[f"vip{fi}_{p}"]
+        assert want.dtype == np.float32
+        assert np.max(np.abs(got - want.astype(np.float64))) < 2e-5     # fp32 reference vs fp64 oracle
+        assert np.argmax(got) == np.argmax(want) or abs(got.max() - want.max()) < 2e-5
+
+
+def test_select_cache_vertices_layout():
+    g = np.load(os.path.join(G, "vip.npz"))
+    vip = O.vip_probabilities(g["rowptr"], g["col"], g["train1"], 32, [15, 10, 5])
+    off = g["offsets"]
+    cv = O.select_cache_vertices(vip, off, 1, 50)
+    assert cv.size == 50 and not np.any((cv >= off[1]) & (cv < off[2]))
+    owner = O.nid2partid(off, cv)
+    assert np.all(np.diff(owner) >= 0)
+    for p in range(4):
+        v = vip[cv[owner == p]]
+        assert np.all(np.diff(v) <= 0)
+    # the 50 selected are the 50 largest remote VIP values
+    remote = np.ones(vip.size, bool)
+    remote[off[1]:off[2]] = False
+    assert np.isclose(np.sort(vip[cv])[0], np.sort(vip[remote])[-50])
