@@ -287,7 +287,16 @@ def ours(args):
     if P > 1:
         x_local = x_full[lo:hi].clone()
         cache_rows = int((n / P) * args.cache_pct / 100.0)
-        cv = S.degree_cache_vertices(rowptr, off.to(dev), rank, cache_rows)
+        if args.cache_policy == "vip":
+            # the reference's policy (driver/drivers/ddp.py:417-446): analytic vertex-inclusion
+            # probabilities of this rank's mini-batches, top remote vertices replicated
+            from salient_plusplus_b200 import vip as V
+            seed_pool = torch.arange(lo, hi, device=dev)  # federated: every local vertex can be a seed
+            probs = V.vip_probabilities(rowptr, col, seed_pool, bs, sizes)
+            cv = V.select_cache_vertices(probs, off, rank, cache_rows)
+            del probs, seed_pool
+        else:
+            cv = S.degree_cache_vertices(rowptr, off.to(dev), rank, cache_rows)
         cache = fs.Cache(rank, P, cv, x_full[cv].contiguous())
         ltab = fs.feature_table(x_local)      # resident copy, 128-byte-multiple row pitch
         ctab = cache.device_table()
@@ -457,7 +466,7 @@ def ours(args):
             "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
             "config": {"workload": desc + (f"; features partitioned {P}-way, {args.cache_pct}% replicated "
-                                           f"degree-ranked cache, P2P gather over NVLink" if P > 1 else ""),
+                                           f"{args.cache_policy}-ranked cache, P2P gather over NVLink" if P > 1 else ""),
                        "graph_generator": "Chung-Lu power law gamma=2.5 head_offset=100 seed=1, symmetrised, deduplicated",
                        "nnz": int(col.numel()), "mean_nodes_per_batch": round(mean_nodes, 1),
                        "streams_in_flight": D, "scale": args.scale, "feature_partitions": P,
@@ -493,9 +502,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (testing only)")
-    ap.add_argument("--depth", type=int, default=4, help="mini-batches in flight (CUDA streams)")
+    ap.add_argument("--depth", type=int, default=6, help="mini-batches in flight (CUDA streams)")
     ap.add_argument("--cache-pct", type=float, default=15.0)
     ap.add_argument("--parts", type=int, default=0, help="feature partitions (default: one per GPU)")
+    ap.add_argument("--cache-policy", default="vip", choices=["vip", "degree"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile the public-API loop (stderr)")
     args = ap.parse_args()

@@ -217,6 +217,10 @@ int spp_sample_hop_fill(const spp_graph* graph_host, int hop, int32_t fanout, in
                         uint64_t rng_seed, int64_t max_targets, int64_t max_edges,
                         const spp_sampler_ws* ws_host, const int64_t* out_rowptr, int64_t* out_col,
                         void* stream);
+/* diagnostics: device buffer (8 uint64 per compaction tile) receiving %globaltimer stamps of the
+ * fused compaction kernel's phases (tools/compact_timeline.py); NULL switches it off */
+void spp_debug_set_timeline(void* dev_ptr);
+
 /* n_id_out[i] = (int64) ws->n_ids[i], i < meta[NODES(hop)]  (or int32 copy if out_is_64 == 0) */
 int spp_sample_export_nids(const spp_sampler_ws* ws_host, int hop, void* n_id_out, int out_is_64,
                            int64_t max_nodes, void* stream);

@@ -30,7 +30,7 @@ EXPORTED = [
     "spp_cache_build_map", "spp_nid_is_cached", "spp_nid2cachenid",
     "spp_split_scratch_words", "spp_split_by_owner",
     "spp_sampler_sizes", "spp_sample_minibatch", "spp_sample_begin", "spp_sample_hop_count",
-    "spp_sample_hop_fill", "spp_sample_export_nids",
+    "spp_sample_hop_fill", "spp_sample_export_nids", "spp_debug_set_timeline",
     "spp_batch_enqueue", "spp_executor_create", "spp_executor_destroy", "spp_executor_submit",
     "spp_executor_poll", "spp_executor_wait", "spp_executor_times",
     "spp_vip_hop",
@@ -128,6 +128,8 @@ def load() -> ctypes.CDLL:
     L.spp_sample_hop_count.argtypes = [POINTER(Graph), ci, i32, ci, i64, POINTER(SamplerWs), vp, vp]
     L.spp_sample_hop_fill.argtypes = [POINTER(Graph), ci, i32, ci, c_uint64, i64, i64,
                                       POINTER(SamplerWs), vp, vp, vp]
+    L.spp_debug_set_timeline.restype = None
+    L.spp_debug_set_timeline.argtypes = [vp]
     L.spp_sample_export_nids.argtypes = [POINTER(SamplerWs), ci, vp, ci, i64, vp]
     L.spp_batch_enqueue.argtypes = [POINTER(BatchJob)]
     L.spp_executor_create.restype = vp

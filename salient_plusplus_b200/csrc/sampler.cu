@@ -591,6 +591,7 @@ struct FusedParams {
   uint32_t* cand;    // uint32[T * k] slot of every virtual candidate
   int64_t cand_cap;  // capacity of cand (elements)
   uint32_t epoch;    // tag of this launch's tile aggregates
+  unsigned long long* timeline;  // diagnostics (spp_debug_set_timeline): 8 globaltimer stamps per tile
 };
 
 // Lane groups of exactly k lanes (32 / k targets per warp) and a three-stage software pipeline
@@ -692,8 +693,19 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __gri
   }
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define SPP_STAMP(i)                                                                         \
+  do {                                                                                       \
+    if (fp.timeline != nullptr && threadIdx.x == 0) fp.timeline[tile * 8 + (i)] = globaltimer_ns(); \
+  } while (0)
+
 __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid_constant__ FusedParams fp) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
+  __shared__ unsigned long long s_red[kScanThreads / 32];
   __shared__ unsigned long long s_base;
   __shared__ int64_t s_tile;
   const HopParams& prm = fp.h;
@@ -722,6 +734,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
     __syncthreads();
     const int64_t tile = s_tile;
     if (tile >= num_tiles) break;
+    SPP_STAMP(0);
     const int64_t v0 = tile * kFusedTile + (int64_t)threadIdx.x * kFusedItems;
     uint32_t slot[kFusedItems];
     uint64_t ent[kFusedItems];
@@ -747,6 +760,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
         if ((uint32_t)(ent[q] >> 32) == ~(Tbase + (uint32_t)(v0 + q))) newm |= 1u << q;
       }
     }
+    SPP_STAMP(1);
     // packed (kept << 16 | new) block scan: per-tile sums are <= 2048 each
     const uint32_t mine = ((uint32_t)__popc(keptm) << 16) | (uint32_t)__popc(newm);
     uint32_t inc = warp_incl_scan(mine, lane);
@@ -761,33 +775,40 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
     }
     const uint32_t texcl = wbase + inc - mine;
     if (threadIdx.x == 0) st_volatile_u64(agg + tile, ((uint64_t)fp.epoch << 32) | (uint64_t)total);
+    SPP_STAMP(2);
     // Sum of the aggregates of every earlier tile (each is published independently of its owner's
-    // own wait, so there is no serial chain).  Only warp 0 polls -- 32 flags per round, with a
-    // back-off -- so that waiting CTAs do not flood L2 with flag reads while the earlier tiles
-    // are still loading their table entries (measured: 256 pollers per CTA tripled the kernel time).
-    if (warp == 0) {
+    // own wait, so there is no serial chain).  Every thread reads its share of the flags at once
+    // (one L2 round trip for the whole CTA); only flags that are not there yet are polled again,
+    // with a back-off, so waiting CTAs do not flood L2 while earlier tiles still load their
+    // table entries (unthrottled polling by 256 threads per CTA tripled the kernel time).
+    {
       unsigned long long acc = 0;  // kept in the high 32 bits, new in the low 32 bits
-      for (int64_t t0 = 0; t0 < tile; t0 += 32) {
-        const int64_t t = t0 + lane;
-        if (t < tile) {
-          uint64_t w = ld_volatile_u64(agg + t);
-          while ((uint32_t)(w >> 32) != fp.epoch) {
-            __nanosleep(64);
-            w = ld_volatile_u64(agg + t);
-          }
-          acc += ((unsigned long long)((uint32_t)w >> 16) << 32) | (unsigned long long)((uint32_t)w & 0xffffu);
+      for (int64_t t = threadIdx.x; t < tile; t += kScanThreads) {
+        uint64_t w = ld_volatile_u64(agg + t);
+        while ((uint32_t)(w >> 32) != fp.epoch) {
+          __nanosleep(64);
+          w = ld_volatile_u64(agg + t);
         }
+        acc += ((unsigned long long)((uint32_t)w >> 16) << 32) | (unsigned long long)((uint32_t)w & 0xffffu);
       }
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFullMask, acc, d);
-      if (lane == 0) s_base = acc;
+      if (lane == 0) s_red[warp] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long b = 0;
+#pragma unroll
+      for (int w = 0; w < kScanThreads / 32; ++w) b += s_red[w];
+      s_base = b;
     }
     __syncthreads();
     const unsigned long long base = s_base;
+    SPP_STAMP(3);
     uint64_t kept_run = (base >> 32) + (texcl >> 16);
     uint64_t new_run = (base & 0xffffffffull) + (texcl & 0xffffu);
     // row bookkeeping: v = i * k + r
-    int64_t row = v0 / k;
+    int64_t row = (int64_t)((uint32_t)v0 / (uint32_t)k);  // V < 2^32 (checked above)
     int r = (int)(v0 - row * k);
 #pragma unroll
     for (int q = 0; q < kFusedItems; ++q) {
@@ -819,6 +840,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
       prm.meta[SPP_META_EDGES(prm.hop)] = (int64_t)kept_total;
       prm.meta[SPP_META_NODES(prm.hop + 1)] = S;
     }
+    SPP_STAMP(4);
     if (num_tiles <= (int64_t)gridDim.x) break;  // every tile has its own CTA: no second ticket
     __syncthreads();                               // s_tile / s_base consumed
     if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd(ctr, 1ull);
@@ -1024,6 +1046,7 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
 }
 
 static std::atomic<uint32_t> g_epoch{1};
+static std::atomic<unsigned long long*> g_timeline{nullptr};
 
 static bool fused_ok(int32_t fanout, int replace, const spp_sampler_ws* ws) {
   return fanout >= 1 && fanout <= 32 && !replace && ws->cand != nullptr;
@@ -1046,6 +1069,7 @@ static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_
     return fail(SPP_ECAPACITY, "sampler: tile_state too small (%lld words needed)", (long long)(2 + tiles));
   fp.cand = reinterpret_cast<uint32_t*>(ws->cand);
   fp.cand_cap = ws->cand_words;
+  fp.timeline = g_timeline.load(std::memory_order_relaxed);
   // epochs stay in [1, 2^30): they can never equal the high word of a look-back state
   // (status << 30) left behind in the shared aggregate area by the general path
   fp.epoch = (g_epoch.fetch_add(1, std::memory_order_relaxed) % 0x3FFFFFFFu) + 1u;
@@ -1094,6 +1118,10 @@ static int launch_export(const spp_sampler_ws* ws, int word, void* out, int out_
 }  // namespace spp
 
 extern "C" {
+
+/* diagnostics: device buffer (8 uint64 per compaction tile) receiving %globaltimer stamps of
+ * k_hop_compact_fused's phases; NULL switches it off */
+void spp_debug_set_timeline(void* dev_ptr) { spp::g_timeline.store((unsigned long long*)dev_ptr); }
 
 int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes, int n_hops, int64_t num_nodes, int64_t max_degree,
                       spp_sampler_sizes_t* out) {

@@ -12,7 +12,7 @@ Differences a caller can observe (all documented in INTEGRATION.md):
     neighbourhoods differ from the reference's mt19937 stream (which is provably non-uniform,
     fast_sampler/sample_cpu.hpp:99); deterministic paths are bit-exact;
   * ``num_threads`` is accepted and ignored: parallelism comes from the GPU, batches are kept in
-    flight on ``min(max_items_in_queue, SPP_SESSION_DEPTH)`` CUDA streams.
+    flight on ``min(max_items_in_queue, SPP_SESSION_DEPTH=6)`` CUDA streams.
 There is no CPU fallback: without a CUDA device or without the built library every entry point
 raises.
 """
@@ -678,7 +678,7 @@ class Session:
         self._row_bytes = self._feat_shape[0] * torch.empty(0, dtype=self._feat_shape[1]).element_size()
         max_bs = max((e - s for s, e in self._ranges), default=0)
         self._sz = _sampler_sizes(max_bs, self._sizes, self._g)
-        depth = int(os.environ.get("SPP_SESSION_DEPTH", "4"))
+        depth = int(os.environ.get("SPP_SESSION_DEPTH", "6"))
         depth = max(1, min(depth, int(max_items_in_queue), max(self._num_total, 1)))
         split_words = int(self._lib.spp_split_scratch_words(self._sz.max_nodes)) if cfg.distributed else 0
         sz = self._sz

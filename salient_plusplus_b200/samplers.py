@@ -112,6 +112,11 @@ class PreparedBatch(NamedTuple):
             adj.record_stream(stream)
 
     def to(self, device, non_blocking=False):
+        # batches are born on the GPU: moving to the device they already live on is the identity
+        dev = torch.device(device)
+        if self.x is not None and self.x.is_cuda and dev.type == "cuda" and \
+                (dev.index is None or dev.index == self.x.device.index):
+            return self
         return PreparedBatch(
             x=self.x.to(device=device, non_blocking=non_blocking) if self.x is not None else None,
             y=self.y.to(device=device, non_blocking=non_blocking) if self.y is not None else None,
