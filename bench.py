@@ -41,6 +41,9 @@ WORKLOADS = {
     "arxiv": ("arxiv", [15, 10, 5], 1024,
               "ogbn-arxiv-shaped synthetic (169K nodes, 1.17M directed edges symmetrised, 128-d fp32), "
               "fanout (15,10,5), batch 1024"),
+    "mag240m": ("mag240m", [25, 15], 1024,
+                "MAG240M-shaped homogeneous synthetic (244M nodes, 1.7B CSR entries = 0.85B directed edges symmetrised, "
+                "768-d fp16), fanout (25,15), batch 1024"),
     "papers100M": ("papers100M", [15, 10, 5], 1024,
                    "ogbn-papers100M-shaped synthetic (111M nodes, 1.6B CSR entries = 0.8B directed edges symmetrised, "
                    "128-d fp16), fanout (15,10,5), batch 1024"),
@@ -125,7 +128,7 @@ def dist_env():
 def make_graph(shape: str, scale: float, device):
     from salient_plusplus_b200 import synthetic as S
     n, e, f, dt = S.SHAPES[shape]
-    if shape == "papers100M":
+    if shape in ("papers100M", "mag240m"):
         e //= 2  # BASELINE's 1.6B is taken as the CSR entry count ("say which")
     n, e = max(1024, int(n * scale)), max(4096, int(e * scale))
     rowptr, col = S.powerlaw_graph(n, e, seed=1, device=device)
@@ -262,9 +265,9 @@ def ours(args):
     K, W = args.steps, args.warmup
     n, f, dt, rowptr, col = make_graph(shape, args.scale, dev)
     col32 = col.to(torch.int32)
-    x_full = S.features(n, f, dt, seed=2, device=dev)
+    del col
     y = S.labels(n, seed=3, device=dev)
-    row_bytes = f * x_full.element_size()
+    row_bytes = f * torch.empty(0, dtype=dt).element_size()
 
     P = max(world, args.parts)
     if P % world != 0:
@@ -281,41 +284,49 @@ def ours(args):
 
     fm = None
     cache = fs.Cache()
-    x_local = x_full
-    cache_rows = 0
     part_tensors = None
+    ptrs = None
+    if world > 1:
+        # one process per GPU: every rank materialises ONLY its own feature partition (a
+        # MAG240M-shaped table is 375 GB in total) ...
+        x_local = S.features(hi - lo, f, dt, seed=2 + rank, device=dev)
+    else:
+        x_full = S.features(n, f, dt, seed=2, device=dev)
+        x_local = x_full if P == 1 else x_full[lo:hi].clone()
     if P > 1:
-        x_local = x_full[lo:hi].clone()
-        cache_rows = int((n / P) * args.cache_pct / 100.0)
-        if args.cache_policy == "vip":
-            # the reference's policy (driver/drivers/ddp.py:417-446): analytic vertex-inclusion
-            # probabilities of this rank's mini-batches, top remote vertices replicated
-            from salient_plusplus_b200 import vip as V
-            seed_pool = torch.arange(lo, hi, device=dev)  # federated: every local vertex can be a seed
-            probs = V.vip_probabilities(rowptr, col, seed_pool, bs, sizes)
-            cv = V.select_cache_vertices(probs, off, rank, cache_rows)
-            del probs, seed_pool
-        else:
-            cv = S.degree_cache_vertices(rowptr, off.to(dev), rank, cache_rows)
-        cache = fs.Cache(rank, P, cv, x_full[cv].contiguous())
+        from salient_plusplus_b200 import peer, vip as V
         ltab = fs.feature_table(x_local)      # resident copy, 128-byte-multiple row pitch
-        ctab = cache.device_table()
-        tables = [None] * P
-        tables[rank] = ltab.storage
         if world > 1:
-            del x_full
-            torch.cuda.empty_cache()
-            from salient_plusplus_b200 import peer
             ptrs = peer.exchange_partition_tables(ltab.storage, rank, P)
             ptrs[rank] = 0
         else:  # every partition lives on this GPU (single-GPU point of a partitioned config)
             part_tensors = [x_full[int(off[p]):int(off[p + 1])] if p != rank else None for p in range(P)]
+        probs = None
+        if args.cache_policy == "vip":
+            # the reference's policy (driver/drivers/ddp.py:417-446): analytic vertex-inclusion
+            # probabilities of this rank's mini-batches (federated: every local vertex can be a seed)
+            probs = V.vip_probabilities(rowptr, col32, torch.arange(lo, hi, device=dev), bs, sizes)
+        else:  # degree ranking (ddp.py:487-495)
+            probs = (rowptr[1:] - rowptr[:-1]).to(torch.float64)
+        # ... and fills its replicated cache by pulling the chosen rows out of the owners'
+        # partitions with the P2P gather kernel (replaces the three blocking all_to_alls of
+        # ddp.py:524-551)
+        cache = V.create_vip_cache(rowptr, col32, None, bs, sizes, off, rank, args.cache_pct, x_local,
+                                   partition_tables=part_tensors, peer_table_ptrs=ptrs, vip=probs)
+        del probs
+        ctab = cache.device_table()
+        tables = [None] * P
+        tables[rank] = ltab.storage
+        if world == 1:
             ptrs = [0] * P
             for p in range(P):
                 if p != rank:
                     tables[p] = fs.feature_table(part_tensors[p]).storage
-        fm = fs.make_feature_map(off.tolist(), rank, tables, ctab.storage, cache.device_map(n), ptrs, ltab.pitch,
-                                 ctab.pitch)
+        fm = fs.make_feature_map(off.tolist(), rank, tables, ctab.storage if ctab else None,
+                                 cache.device_map(n) if ctab else None, ptrs, ltab.pitch, ctab.pitch if ctab else 0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
 
     pipe = MiniBatchPipeline(rowptr, col32, sizes, bs, x_table=None if fm is not None else x_local, y_table=y,
                              feature_map=fm, feat_dim=f, feat_dtype=dt, split=False, depth=args.depth, device=dev)
@@ -451,7 +462,7 @@ def ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cb = min(K + W, 96)
-        bps, gbs, timed, kind, _ = run_reference_cpu(rowptr.cpu(), col.cpu(), x_local.cpu(), y.cpu(),
+        bps, gbs, timed, kind, _ = run_reference_cpu(rowptr.cpu(), col32.to(torch.int64).cpu(), x_local.cpu(), y.cpu(),
                                                      idx_host[:(cb + 8) * bs].clone(), sizes, bs, threads, 8, cb,
                                                      max_seconds=25.0)
         cpu = {"value": round(bps, 3), "unit": UNIT, "cores": threads, "kind": kind, "gathered_GBps": round(gbs, 3),
@@ -468,7 +479,7 @@ def ours(args):
             "config": {"workload": desc + (f"; features partitioned {P}-way, {args.cache_pct}% replicated "
                                            f"{args.cache_policy}-ranked cache, P2P gather over NVLink" if P > 1 else ""),
                        "graph_generator": "Chung-Lu power law gamma=2.5 head_offset=100 seed=1, symmetrised, deduplicated",
-                       "nnz": int(col.numel()), "mean_nodes_per_batch": round(mean_nodes, 1),
+                       "nnz": int(col32.numel()), "mean_nodes_per_batch": round(mean_nodes, 1),
                        "streams_in_flight": D, "scale": args.scale, "feature_partitions": P,
                        "l2": "inputs larger than L2 (feature table + CSR >> 126 MB, random rows)"},
             "gathered_GBps": round(value * mean_nodes * row_bytes / 1e9, 2),

@@ -76,6 +76,7 @@ def create_vip_cache(rowptr: torch.Tensor, col: torch.Tensor, train_idx_local: t
     n = rowptr.numel() - 1
     if vip is None:
         vip = vip_probabilities(rowptr, col, train_idx_local, batch_size, fanouts)
+    # `vip` may be any per-vertex score (e.g. degrees for cache_strategy == "degree", ddp.py:487-495)
     num = int(n / P * (cache_pct / 100.0))                     # ddp.py:421
     cv = select_cache_vertices(vip, partition_offsets, rank, num)
     ltab = feature_table(local_features)
