@@ -93,3 +93,33 @@ def test_no_cuda_device_fails_loudly():
     from salient_plusplus_b200 import fast_sampler as fs
     with pytest.raises(RuntimeError):
         fs.serial_index(torch.zeros(4, 4), torch.tensor([0]))
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 and a C program must link
+    against the library and call a host-only entry point (no GPU needed)."""
+    import subprocess
+    from salient_plusplus_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text('''
+#include <stdio.h>
+#include "salient_b200.h"
+int main(void) {
+  spp_sampler_sizes_t s;
+  int32_t sizes[3] = {15, 10, 5};
+  if (spp_abi_version() != SPP_ABI_VERSION) return 1;
+  if (spp_sampler_sizes(1024, sizes, 3, 0, 0, &s) != 0) return 2;
+  if (s.max_nodes != 1081344) return 3;
+  if (spp_gather_rows(0, 0, 0, 1, 1, 0, 0, 1, 0) == 0) return 4;   /* bad row_bytes must fail */
+  printf("%s\\n", spp_last_error());
+  return sizeof(spp_batch_job) == 824 ? 0 : 5;
+}
+''')
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libsalient_b200.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "row_bytes" in out.stdout
