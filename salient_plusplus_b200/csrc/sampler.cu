@@ -1076,7 +1076,14 @@ static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_
   const bool c64 = g->col_is_64 != 0;
   const int sms = num_sms();
   const int G = fanout <= 4 ? 4 : fanout <= 8 ? 8 : fanout <= 16 ? 16 : 32;  // relabel/sort groups (power of two)
-  const int64_t cap = (int64_t)sms * 8;
+  static int s_cps = 0, r_cps = 0;  // CTAs per SM of the sampling / relabel kernels (tunable for experiments)
+  if (s_cps == 0) {
+    const char* e = getenv("SPP_SAMPLE_CTAS_PER_SM");
+    s_cps = (e && atoi(e) > 0) ? atoi(e) : 8;
+    e = getenv("SPP_RELABEL_CTAS_PER_SM");
+    r_cps = (e && atoi(e) > 0) ? atoi(e) : 8;
+  }
+  int64_t cap = (int64_t)sms * s_cps;
   {
     const int gpw = 32 / fanout;
     int64_t warps = ceil_div(fp.h.max_targets > 0 ? fp.h.max_targets : 1, gpw);
@@ -1085,6 +1092,7 @@ static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_
     if (c64) k_hop_sample_fused<true><<<sgrid, kSampleThreads, 0, st>>>(fp);
     else k_hop_sample_fused<false><<<sgrid, kSampleThreads, 0, st>>>(fp);
   }
+  cap = (int64_t)sms * r_cps;
   int64_t warps = ceil_div(fp.h.max_targets > 0 ? fp.h.max_targets : 1, 32 / G);
   int64_t ctas = ceil_div(warps, kSampleThreads / 32);
   const int grid = (int)(ctas < cap ? ctas : cap);
