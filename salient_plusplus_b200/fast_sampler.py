@@ -662,6 +662,7 @@ class Session:
             self._idx, self._idx_host = idx, None
         else:
             self._idx, self._idx_host = None, idx
+            self._idx_host_ptr = idx.data_ptr()
         self._ranges = _batch_ranges(idx.numel(), cfg)
         self._num_total = len(self._ranges)
         self._num_consumed = 0
@@ -698,6 +699,10 @@ class Session:
         self._arena_nid = o
         if cfg.distributed:
             o += 3 * int(sz.max_nodes)  # n_id, bucket_ids, perm
+        self._y_in_arena = self._y is not None and self._y.dtype == torch.int64
+        self._arena_y = o
+        if self._y_in_arena:
+            o += max_bs * self._y.size(-1)
         self._arena_words = max(o, 1)
         self._executor = None
         if not self._full and os.environ.get("SPP_EXECUTOR", "1") != "0":
@@ -934,15 +939,25 @@ class Session:
                     x = torch.empty((ws.max_nodes, fdim), dtype=fdtype, device=self._device)
                 y = None
                 if self._y is not None:
-                    y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
+                    if self._y_in_arena:  # int64 labels live at the tail of the arena
+                        yo = self._arena_y
+                        y = arena[yo:yo + bs * self._y.size(-1)].view(bs, self._y.size(-1))
+                    else:
+                        y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
             base = arena.data_ptr()
             for h, (ro, co) in enumerate(self._arena_off):
                 j.out_rowptr[h] = base + 8 * ro
                 j.out_col[h] = base + 8 * co
             if self._idx_host is not None:
-                if bs:
-                    slot.seeds_host[:bs].copy_(self._idx_host[start:stop])
-                j.seeds_host = slot.seeds_host.data_ptr() if bs else None
+                # the executor thread copies straight out of the caller's idx memory (an 8 KB
+                # cudaMemcpyAsync; pageable sources are staged by the driver); the Session keeps
+                # idx alive.  Without the executor the pinned per-slot staging buffer is used.
+                if self._executor is not None:
+                    j.seeds_host = self._idx_host_ptr + 8 * start if bs else None
+                else:
+                    if bs:
+                        slot.seeds_host[:bs].copy_(self._idx_host[start:stop])
+                    j.seeds_host = slot.seeds_host.data_ptr() if bs else None
                 j.seeds_dev = slot.seeds.data_ptr()
             else:
                 j.seeds_host = None
