@@ -72,9 +72,9 @@ def _worker(rank, world, port, ret):
 def test_two_ranks_gloo():
     world = 2
     port = 29500 + (os.getpid() % 400)
-    mgr = mp.Manager()
-    ret = mgr.dict()
     ctx = mp.get_context("spawn")
+    mgr = ctx.Manager()
+    ret = mgr.dict()
     procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
     for p in procs:
         p.start()
