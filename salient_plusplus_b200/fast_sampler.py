@@ -775,7 +775,9 @@ class Session:
         self._x_local = local
         ref = xg if has_g else xc
         self._feat_shape = (ref.size(-1), ref.dtype) if ref.dim() == 2 else (0, torch.float16)
-        self._use_cache = bool(cfg.use_cache)
+        # an empty cache makes the cache branch (fast_sampler.cpp:1108-1260) produce exactly what the
+        # no-cache branch (:1031-1107) produces, so it takes the kernel path without a cache map
+        self._use_cache = bool(cfg.use_cache) and cfg.cache.cached_vertices.numel() > 0
         self._cache_map = cfg.cache.device_map(self._g.num_nodes) if self._use_cache else None
         self._cache_feats = cfg.cache.device_features() if self._use_cache else None
         # book-only map for the split kernel

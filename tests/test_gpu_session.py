@@ -116,3 +116,98 @@ def test_session_distributed_single_process(fs, data, use_cache, P, rank):
         assert np.array_equal(b.n_id.cpu().numpy(), on)
         assert torch.equal(b.x.cpu(), x[torch.from_numpy(on)])
     assert sess.blocking_get_batch_distributed() is None
+
+
+def _random_multigraph(rng, n, max_deg):
+    rowptr, col = [0], []
+    for _ in range(n):
+        d = int(rng.integers(0, max_deg + 1))
+        col.extend(rng.integers(0, n, size=d).tolist())       # unsorted, duplicate neighbours, self loops
+        rowptr.append(len(col))
+    return torch.tensor(rowptr, dtype=torch.int64), torch.tensor(col, dtype=torch.int64)
+
+
+@pytest.mark.parametrize("case", range(32))
+def test_randomized_sessions_against_oracle(fs, case):
+    """Seeded sweep mirroring tests/test_oracle_vs_ref.py: random multigraphs (isolated nodes, self
+    loops, duplicate neighbours), duplicate seeds, every fan-out regime incl. > 32 and full
+    neighbourhood, mixed hops, both batch-range modes, host or device idx -- bit-exact."""
+    rng = np.random.default_rng(5000 + case)
+    n = int(rng.integers(5, 600))
+    rowptr, col = _random_multigraph(rng, n, int(rng.integers(0, 60)))
+    L = int(rng.integers(1, 4))
+    sizes = [int(rng.choice([-1, 1, 2, 5, 15, 25, 40, 100])) for _ in range(L)]
+    idx = torch.from_numpy(rng.integers(0, n, size=int(rng.integers(1, 300)))).to(torch.int64)
+    x = torch.from_numpy(rng.integers(0, 1000, size=(n, int(rng.choice([3, 50, 64]))))).to(torch.float16)
+    y = torch.from_numpy(rng.integers(0, 9, size=(n, 1)))
+    cfg = fs.Config()
+    cfg.x_cpu, cfg.y, cfg.rowptr, cfg.col = x, y, rowptr, col
+    cfg.idx = idx.cuda() if case % 3 == 0 else idx
+    cfg.batch_size, cfg.sizes = int(rng.integers(1, 128)), sizes
+    cfg.skip_nonfull_batch = bool(rng.integers(0, 2))
+    exact = bool(rng.integers(0, 2)) and idx.numel() >= 8
+    cfg.force_exact_num_batches, cfg.exact_num_batches = exact, (int(rng.integers(1, 5)) if exact else 0)
+    sess = fs.Session(1, int(rng.integers(1, 9)), cfg)
+    want_ranges = O.batch_ranges(idx.numel(), cfg.batch_size, cfg.skip_nonfull_batch, exact, cfg.exact_num_batches)
+    assert sess.num_total_batches == len(want_ranges)
+    got = []
+    while True:
+        b = sess.blocking_get_batch()
+        if b is None:
+            break
+        xb, yb, adjs, (st, en) = b
+        got.append((st, en))
+        on, oa = O.multilayer_sample(idx[st:en].numpy(), sizes, rowptr.numpy(), col.numpy(), rng_mode=O.RNG_COUNTER,
+                                     rng_seed=O.session_rng_seed(en))
+        assert adjs_equal(adjs, oa), (case, sizes, (st, en))
+        assert torch.equal(xb.cpu(), x[torch.from_numpy(on)])
+        assert torch.equal(yb.cpu(), y[idx[st:en]].view(-1, 1))
+    assert got == want_ranges
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_randomized_distributed_sessions_against_oracle(fs, case):
+    """Random partition counts / ranks / caches / x_gpu-x_cpu cut-offs: every ProtoDistributedBatch
+    field against the oracle's restatement of fast_sampler.cpp:1017-1262, and x == X[n_id]."""
+    rng = np.random.default_rng(9000 + case)
+    n = int(rng.integers(40, 800))
+    rowptr, col = _random_multigraph(rng, n, int(rng.integers(1, 40)))
+    P = int(rng.choice([1, 2, 3, 4, 8, 16]))
+    cuts = np.sort(rng.integers(0, n + 1, size=P - 1)) if P > 1 else np.empty(0, dtype=np.int64)
+    off = torch.tensor([0] + cuts.tolist() + [n], dtype=torch.int64)          # ragged, possibly empty partitions
+    sizes_p = (off[1:] - off[:-1]).tolist()
+    rank = int(rng.choice([p for p in range(P) if sizes_p[p] > 0]))
+    lo, hi = int(off[rank]), int(off[rank + 1])
+    x = torch.from_numpy(rng.integers(0, 1000, size=(n, int(rng.choice([4, 50, 64]))))).to(torch.float16)
+    y = torch.from_numpy(rng.integers(0, 9, size=(n, 1)))
+    idx = torch.from_numpy(rng.integers(lo, hi, size=int(rng.integers(1, 200)))).to(torch.int64)
+    use_cache = bool(rng.integers(0, 2)) and P > 1
+    remote = np.setdiff1d(np.arange(n), np.arange(lo, hi))
+    cv = torch.from_numpy(rng.permutation(remote)[:int(rng.integers(0, max(1, remote.size // 2) + 1))]).to(torch.int64)
+    cut = int(rng.integers(0, hi - lo + 1))
+    sizes = [int(rng.choice([2, 5, 15, 40])) for _ in range(int(rng.integers(1, 4)))]
+    cfg = fs.Config()
+    cfg.x_gpu, cfg.x_cpu, cfg.y = x[lo:lo + cut].contiguous(), x[lo + cut:hi].contiguous(), y
+    cfg.rowptr, cfg.col, cfg.idx = rowptr, col, idx
+    cfg.batch_size, cfg.sizes, cfg.distributed, cfg.use_cache = int(rng.integers(1, 96)), sizes, True, use_cache
+    cfg.partition_book = fs.RangePartitionBook(rank, P, off)
+    cfg.cache = fs.Cache(rank, P, cv, x[cv].contiguous()) if use_cache else fs.Cache()
+    cfg.partition_tables = [x[int(off[p]):int(off[p + 1])].contiguous() if p != rank and sizes_p[p] > 0 else None
+                            for p in range(P)]
+    sess = fs.Session(1, 4, cfg)
+    oc = O.Cache(cv.numpy(), n) if use_cache else None
+    for st, en in O.batch_ranges(idx.numel(), cfg.batch_size):
+        b = sess.blocking_get_batch_distributed()
+        assert tuple(b.idx_range) == (st, en)
+        on, oa = O.multilayer_sample(idx[st:en].numpy(), sizes, rowptr.numpy(), col.numpy(), rng_mode=O.RNG_COUNTER,
+                                     rng_seed=O.session_rng_seed(en))
+        pn, cn, perm, loc_cpu = O.distributed_binning(on, off.numpy(), rank, P, cut, use_cache, oc)
+        assert adjs_equal(b.adjs, oa)
+        for a, w in zip(b.partition_nids, pn):
+            assert np.array_equal(a.cpu().numpy(), w)
+        assert np.array_equal(b.cached_nids.cpu().numpy(), cn)
+        assert np.array_equal(b.perm_partition_to_mfg.cpu().numpy(), perm)
+        assert torch.equal(b.sliced_cpu_features.cpu(), cfg.x_cpu[torch.from_numpy(loc_cpu)])
+        assert torch.equal(b.sliced_cpu_labels.cpu(), y[idx[st:en]].view(-1, 1))
+        assert torch.equal(b.x.cpu(), x[torch.from_numpy(on)])
+    assert sess.blocking_get_batch_distributed() is None

@@ -81,3 +81,53 @@ def test_partition_book(R):
         assert np.array_equal(book.nid2partid(nids).numpy(), O.nid2partid(off.numpy(), nids.numpy()))
         assert np.array_equal(book.nid2localnid(nids, P - 1).numpy(), O.nid2localnid(off.numpy(), nids.numpy(), P - 1))
         assert np.array_equal(book.partid2nids(0).numpy(), O.partid2nids(off.numpy(), 0))
+
+
+def _random_graph(rng, n, max_deg):
+    rowptr = [0]
+    col = []
+    for _ in range(n):
+        d = int(rng.integers(0, max_deg + 1))
+        col.extend(rng.integers(0, n, size=d).tolist())   # unsorted, duplicates and self loops allowed
+        rowptr.append(len(col))
+    return torch.tensor(rowptr, dtype=torch.int64), torch.tensor(col, dtype=torch.int64)
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_randomized_sessions_against_reference(R, case):
+    """Seeded sweep: tiny to medium random multigraphs (isolated nodes, self loops, duplicate
+    neighbours), duplicate seeds, every fan-out regime (full, fan-out >= degree, Floyd), both batch
+    range modes -- oracle == compiled reference, field by field."""
+    rng = np.random.default_rng(1000 + case)
+    n = int(rng.integers(5, 400))
+    rowptr, col = _random_graph(rng, n, int(rng.integers(0, 30)))
+    L = int(rng.integers(1, 4))
+    sizes = [int(rng.choice([-1, 1, 2, 5, 15, 40])) for _ in range(L)]
+    idx = torch.from_numpy(rng.integers(0, n, size=int(rng.integers(1, 150)))).to(torch.int64)  # duplicates likely
+    x = torch.from_numpy(rng.integers(0, 1000, size=(n, 3))).to(torch.float16)
+    y = torch.from_numpy(rng.integers(0, 9, size=(n, 1)))
+    cfg = R.Config()
+    cfg.x_cpu, cfg.x_gpu, cfg.y = x, torch.empty(0), y
+    cfg.rowptr, cfg.col, cfg.idx = rowptr, col, idx
+    cfg.batch_size, cfg.sizes = int(rng.integers(1, 64)), sizes
+    cfg.skip_nonfull_batch = bool(rng.integers(0, 2))
+    cfg.pin_memory = cfg.distributed = False
+    exact = bool(rng.integers(0, 2)) and idx.numel() >= 8
+    cfg.force_exact_num_batches, cfg.exact_num_batches = exact, (int(rng.integers(1, 5)) if exact else 0)
+    cfg.count_remote_frequency = cfg.use_cache = False
+    s = R.Session(2, 8, cfg)
+    want_ranges = O.batch_ranges(idx.numel(), cfg.batch_size, cfg.skip_nonfull_batch, exact, cfg.exact_num_batches)
+    assert s.num_total_batches == len(want_ranges)
+    got = []
+    while True:
+        b = s.blocking_get_batch()
+        if b is None:
+            break
+        xb, yb, adjs, (st, en) = b
+        got.append((st, en))
+        on, oa = O.multilayer_sample(idx[st:en].numpy(), sizes, rowptr.numpy(), col.numpy(), rng_mode=O.RNG_REFERENCE,
+                                     rng_seed=O.session_rng_seed(en))
+        assert same(adjs, oa), (case, sizes)
+        assert np.array_equal(xb.view(torch.int16).numpy(), x.view(torch.int16).numpy()[on])
+        assert np.array_equal(yb.numpy(), y.numpy()[idx[st:en].numpy()])
+    assert sorted(got) == want_ranges
