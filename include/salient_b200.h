@@ -176,10 +176,10 @@ typedef struct spp_sampler_sizes_t {
 } spp_sampler_sizes_t;
 
 /* Upper bounds for a batch of `batch_size` seeds and fanouts `sizes` (negative = all
- * neighbours).  For full-neighbourhood hops the bounds need the graph: pass max_degree
+ * neighbours; replace != 0: k draws with replacement, i.e. k edges even when deg < k).  For full-neighbourhood hops the bounds need the graph: pass max_degree
  * (any upper bound on the degree) and num_nodes; edges bound = targets * max_degree. */
-int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes_host, int n_hops, int64_t num_nodes,
-                      int64_t max_degree, spp_sampler_sizes_t* out_host);
+int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes_host, int n_hops, int replace,
+                      int64_t num_nodes, int64_t max_degree, spp_sampler_sizes_t* out_host);
 
 /* One mini-batch, all hops, no host synchronisation:
  *   seeds        int64[batch_size]  (global ids; duplicates allowed, last position wins in the

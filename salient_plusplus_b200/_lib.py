@@ -120,7 +120,7 @@ def load() -> ctypes.CDLL:
     L.spp_split_scratch_words.restype = i64
     L.spp_split_scratch_words.argtypes = [i64]
     L.spp_split_by_owner.argtypes = [POINTER(FeatureMap), ci, vp, ci, i64, vp, vp, vp, vp, vp, vp]
-    L.spp_sampler_sizes.argtypes = [i64, POINTER(i32), ci, i64, i64, POINTER(SamplerSizes)]
+    L.spp_sampler_sizes.argtypes = [i64, POINTER(i32), ci, ci, i64, i64, POINTER(SamplerSizes)]
     L.spp_sample_minibatch.argtypes = [POINTER(Graph), vp, i64, POINTER(i32), ci, ci, c_uint64,
                                        POINTER(SamplerWs), POINTER(vp), POINTER(vp), POINTER(i64),
                                        vp, vp]

@@ -1131,8 +1131,8 @@ extern "C" {
  * k_hop_compact_fused's phases; NULL switches it off */
 void spp_debug_set_timeline(void* dev_ptr) { spp::g_timeline.store((unsigned long long*)dev_ptr); }
 
-int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes, int n_hops, int64_t num_nodes, int64_t max_degree,
-                      spp_sampler_sizes_t* out) {
+int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes, int n_hops, int replace, int64_t num_nodes,
+                      int64_t max_degree, spp_sampler_sizes_t* out) {
   using namespace spp;
   if (!out || (n_hops > 0 && !sizes)) return fail(SPP_EINVAL, "spp_sampler_sizes: null argument");
   if (n_hops < 0 || n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_sampler_sizes: n_hops %d out of range", n_hops);
@@ -1145,7 +1145,8 @@ int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes, int n_hops, int6
     int64_t k = sizes[h];
     int64_t E;
     if (k >= 0) {
-      int64_t per = (max_degree > 0 && max_degree < k) ? max_degree : k;
+      // without replacement a target keeps min(k, deg) edges; with replacement always k
+      int64_t per = (!replace && max_degree > 0 && max_degree < k) ? max_degree : k;
       E = T * per;
     } else if (max_degree >= 0) {
       E = T * max_degree;

@@ -169,12 +169,12 @@ class _DeviceGraph:
         return g
 
 
-def _sampler_sizes(bs: int, sizes: Sequence[int], g: _DeviceGraph) -> SamplerSizes:
+def _sampler_sizes(bs: int, sizes: Sequence[int], g: _DeviceGraph, replace: bool = False) -> SamplerSizes:
     L = len(sizes)
     arr = (ctypes.c_int32 * max(L, 1))(*[int(s) for s in sizes])
     out = SamplerSizes()
-    check(_lib.load().spp_sampler_sizes(int(bs), arr, L, g.num_nodes, g.max_degree, ctypes.byref(out)),
-          "spp_sampler_sizes")
+    check(_lib.load().spp_sampler_sizes(int(bs), arr, L, int(bool(replace)), g.num_nodes, g.max_degree,
+                                        ctypes.byref(out)), "spp_sampler_sizes")
     return out
 
 
@@ -295,7 +295,7 @@ def _sample(rowptr, col, idx, sizes: Sequence[int], replace: bool, seed: Optiona
         raise RuntimeError(f"at most {SPP_MAX_HOPS} hops are supported")
     g = _DeviceGraph.get(rowptr, col)
     seeds = idx.to(device=device, dtype=torch.int64).contiguous()
-    sz = _sampler_sizes(seeds.numel(), sizes, g)
+    sz = _sampler_sizes(seeds.numel(), sizes, g, replace)
     ws = _Workspace(sz, device)
     rng_seed = _next_free_seed() if seed is None else int(seed)
     if any(int(s) < 0 for s in sizes):

@@ -45,18 +45,21 @@ def test_sampler_sizes_host_only(lib):
     from salient_plusplus_b200 import _lib
     out = _lib.SamplerSizes()
     sizes = (ctypes.c_int32 * 3)(15, 10, 5)
-    assert lib.spp_sampler_sizes(1024, sizes, 3, 0, 0, ctypes.byref(out)) == 0
+    assert lib.spp_sampler_sizes(1024, sizes, 3, 0, 0, 0, ctypes.byref(out)) == 0
     assert list(out.hop_targets)[:3] == [1024, 16384, 180224]
     assert list(out.hop_edges)[:3] == [15360, 163840, 901120]
     assert out.max_nodes == 1081344 and out.max_targets == 180224
     assert out.table_slots == 2097152 and out.cand_words == 901120 + 16
     # node bound capped by the graph size, edge bound by the maximum degree
-    assert lib.spp_sampler_sizes(1024, sizes, 3, 100000, 7, ctypes.byref(out)) == 0
+    assert lib.spp_sampler_sizes(1024, sizes, 3, 0, 100000, 7, ctypes.byref(out)) == 0
     assert out.max_nodes == 101024 and list(out.hop_edges)[:3] == [1024 * 7, 8192 * 7, 65536 * 5]
+    # with replacement every target with a neighbour emits exactly k edges: no max_degree tightening
+    assert lib.spp_sampler_sizes(1024, sizes, 3, 1, 100000, 7, ctypes.byref(out)) == 0
+    assert list(out.hop_edges)[:2] == [15360, 163840]
     full = (ctypes.c_int32 * 1)(-1)
-    assert lib.spp_sampler_sizes(8, full, 1, 100, -1, ctypes.byref(out)) == _lib.SPP_EINVAL if hasattr(_lib, "SPP_EINVAL") else True
-    assert lib.spp_sampler_sizes(8, full, 1, 100, 9, ctypes.byref(out)) == 0 and out.hop_edges[0] == 72
-    assert lib.spp_sampler_sizes(8, sizes, 99, 0, 0, ctypes.byref(out)) != 0
+    assert lib.spp_sampler_sizes(8, full, 1, 0, 100, -1, ctypes.byref(out)) == _lib.SPP_EINVAL if hasattr(_lib, "SPP_EINVAL") else True
+    assert lib.spp_sampler_sizes(8, full, 1, 0, 100, 9, ctypes.byref(out)) == 0 and out.hop_edges[0] == 72
+    assert lib.spp_sampler_sizes(8, sizes, 99, 0, 0, 0, ctypes.byref(out)) != 0
     assert b"n_hops" in lib.spp_last_error()
     assert lib.spp_split_scratch_words(0) > 0 and lib.spp_split_scratch_words(10 ** 6) > 10 ** 6 // 4
 
@@ -108,7 +111,7 @@ int main(void) {
   spp_sampler_sizes_t s;
   int32_t sizes[3] = {15, 10, 5};
   if (spp_abi_version() != SPP_ABI_VERSION) return 1;
-  if (spp_sampler_sizes(1024, sizes, 3, 0, 0, &s) != 0) return 2;
+  if (spp_sampler_sizes(1024, sizes, 3, 0, 0, 0, &s) != 0) return 2;
   if (s.max_nodes != 1081344) return 3;
   if (spp_gather_rows(0, 0, 0, 1, 1, 0, 0, 1, 0) == 0) return 4;   /* bad row_bytes must fail */
   printf("%s\\n", spp_last_error());

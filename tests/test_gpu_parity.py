@@ -377,3 +377,74 @@ def test_gather_rows_pitched(fs, dim, dtype, pitch_elems):
     if dim * es == 200:
         assert t.pitch == 256
         assert torch.equal(t.storage[:, :dim].cpu(), dense)
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_randomized_gather_alignment_and_shapes(fs, case):
+    """Random row sizes (1..1500 bytes), misaligned table / output bases (exercises the 16/8/4/2/1
+    byte vector paths), pitched sources, int32/int64 indices, device-side row count."""
+    from salient_plusplus_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(7000 + case)
+    row_bytes = int(rng.choice([1, 2, 3, 4, 6, 8, 12, 16, 24, 100, 200, 256, 264, 512, 1000, 1500]))
+    pitch = row_bytes + int(rng.choice([0, 0, 8, 56, 13])) if row_bytes > 1 else row_bytes
+    n_rows, n_idx = int(rng.integers(1, 3000)), int(rng.integers(0, 5000))
+    src_off, dst_off = int(rng.choice([0, 0, 1, 2, 4, 8, 16])), int(rng.choice([0, 0, 1, 2, 4, 8, 16]))
+    tbuf = torch.from_numpy(rng.integers(0, 256, size=n_rows * pitch + 64, dtype=np.uint8)).cuda()
+    table = tbuf[src_off:src_off + n_rows * pitch]
+    idx64 = torch.from_numpy(rng.integers(0, n_rows, size=n_idx)).to(torch.int64)
+    use64 = bool(rng.integers(0, 2))
+    idx = (idx64 if use64 else idx64.to(torch.int32)).cuda()
+    n_out = max(1, int(n_idx * rng.choice([0.5, 1.0, 1.5])))
+    obuf = torch.full((n_out * row_bytes + 64,), 0xAB, dtype=torch.uint8, device="cuda")
+    out = obuf[dst_off:dst_off + n_out * row_bytes]
+    n_dev = None
+    n_eff = min(n_idx, n_out)
+    if rng.integers(0, 2):
+        n_eff = int(rng.integers(0, n_eff + 1))
+        n_dev = torch.tensor([n_eff], dtype=torch.int64, device="cuda")
+    _lib.check(L.spp_gather_rows_pitched(table.data_ptr(), pitch, row_bytes, idx.data_ptr(), int(use64), n_idx,
+                                         n_dev.data_ptr() if n_dev is not None else None, out.data_ptr(), n_out,
+                                         torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    t2 = table.cpu().view(n_rows, pitch)[:, :row_bytes]
+    want = t2[idx64[:n_eff]]
+    got = out.cpu().view(n_out, row_bytes)
+    assert torch.equal(got[:n_eff], want)
+    assert bool((got[n_eff:] == 0xAB).all())                      # nothing written past the row count
+    assert bool((obuf[:dst_off] == 0xAB).all()) and bool((obuf[dst_off + n_out * row_bytes:] == 0xAB).all())
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_randomized_book_cache_and_sample_adj(fs, case):
+    rng = np.random.default_rng(8000 + case)
+    N = int(rng.integers(10, 5000))
+    P = int(rng.choice([1, 2, 5, 8, 16]))
+    cuts = np.sort(rng.integers(0, N + 1, size=P - 1)) if P > 1 else np.empty(0, dtype=np.int64)
+    off = torch.tensor([0] + cuts.tolist() + [N], dtype=torch.int64)       # ragged / empty partitions
+    nids = torch.from_numpy(rng.integers(0, N, size=int(rng.integers(0, 3000)))).to(torch.int64)
+    rank = int(rng.integers(0, P))
+    book = fs.RangePartitionBook(rank, P, off)
+    assert np.array_equal(book.nid2partid(nids).numpy(), O.nid2partid(off.numpy(), nids.numpy()))
+    assert np.array_equal(book.nid2localnid(nids, rank).numpy(), O.nid2localnid(off.numpy(), nids.numpy(), rank))
+    assert np.array_equal(book.nid_is_local(nids).numpy(), O.nid_is_local(off.numpy(), rank, nids.numpy()))
+    cv = torch.from_numpy(rng.integers(0, N, size=int(rng.integers(0, N)))).to(torch.int64)   # duplicates allowed
+    c, oc = fs.Cache(rank, P, cv, torch.zeros(cv.numel(), 2).half()), O.Cache(cv.numpy(), N)
+    assert np.array_equal(c.nid_is_cached(nids).numpy(), oc.nid_is_cached(nids.numpy()))
+    hit = nids[c.nid_is_cached(nids)]
+    assert np.array_equal(c.nid2cachenid(hit).numpy(), oc.nid2cachenid(hit.numpy()))
+    # one-hop sample_adj in all three modes on a random multigraph
+    n = int(rng.integers(5, 300))
+    rowptr, col = [0], []
+    for _ in range(n):
+        d = int(rng.integers(0, 50))
+        col.extend(rng.integers(0, n, size=d).tolist())
+        rowptr.append(len(col))
+    rowptr, col = torch.tensor(rowptr), torch.tensor(col, dtype=torch.int64)
+    idx = torch.from_numpy(rng.integers(0, n, size=int(rng.integers(1, 100)))).to(torch.int64)
+    for k, rep in ((-1, False), (int(rng.integers(1, 60)), False), (int(rng.integers(1, 60)), True)):
+        rp, cl, n_id, _ = fs.sample_adj(rowptr, col, idx, k, rep, seed=99 + case)
+        orp, ocl, on, _ = O.sample_adj(rowptr.numpy(), col.numpy(), idx.numpy(), k, rep, rng_mode=O.RNG_COUNTER,
+                                       rng_seed=99 + case)
+        assert np.array_equal(rp.cpu().numpy(), orp) and np.array_equal(cl.cpu().numpy(), ocl)
+        assert np.array_equal(n_id.cpu().numpy(), on)
