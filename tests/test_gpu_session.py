@@ -211,3 +211,57 @@ def test_randomized_distributed_sessions_against_oracle(fs, case):
         assert torch.equal(b.sliced_cpu_labels.cpu(), y[idx[st:en]].view(-1, 1))
         assert torch.equal(b.x.cpu(), x[torch.from_numpy(on)])
     assert sess.blocking_get_batch_distributed() is None
+
+
+def test_session_api_behaviour(fs, data):
+    """try_get_batch, abandoning a Session mid-epoch, slot reuse across Sessions, the slice API,
+    wrong-mode calls and unsupported fan-outs failing loudly."""
+    rowptr, col, x, y, N = data
+    idx = S.seeds(N, 640)
+    cfg = _config(fs, x, y, rowptr, col, idx)
+    s1 = fs.Session(8, 2, cfg)
+    first = s1.blocking_get_batch()
+    assert first[3] == (0, 64) and s1.num_consumed_batches == 1 and s1.num_total_batches == 10
+    assert s1.approx_num_complete_batches >= 1
+    with pytest.raises(RuntimeError):
+        s1.blocking_get_batch_distributed()
+    del s1                                                    # dropped with batches still in flight
+    s2 = fs.Session(8, 2, cfg)                                # picks the pooled slots up again
+    seen = 0
+    import time as _t
+    deadline = _t.time() + 30
+    while seen < 10 and _t.time() < deadline:                 # non-blocking polling like the reference's try_get_batch
+        b = s2.try_get_batch()
+        if b is not None:
+            assert b[3] == (64 * seen, 64 * seen + 64)
+            seen += 1
+    assert seen == 10 and s2.try_get_batch() is None and s2.blocking_get_batch() is None
+    # fan-out beyond SPP_MAX_FANOUT without replacement is refused, not silently truncated
+    with pytest.raises(RuntimeError):
+        fs.multilayer_sample(idx[:8], [200], rowptr, col)
+    with pytest.raises(RuntimeError):
+        fs.multilayer_sample(idx[:8], [5] * 9, rowptr, col)   # more than SPP_MAX_HOPS hops
+    # full_sample is a documented stub
+    with pytest.raises(RuntimeError):
+        fs.full_sample()
+
+
+def test_async_slice_tensors_contract(fs, data):
+    """fast_sampler.cpp:720-758: per requester [rows of x_cpu for ids >= 0, positions of ids >= 0,
+    positions of ids < 0]; own rank gets an empty first element."""
+    rowptr, col, x, y, N = data
+    P, rank = 2, 0
+    off = S.equal_partition_offsets(N, P)
+    hi = int(off[1])
+    cut = hi // 2
+    cfg = _config(fs, x[cut:hi].contiguous(), y, rowptr, col, S.seeds(N, 64, lo=0, hi=hi), distributed=True)
+    cfg.x_gpu = x[:cut].contiguous()
+    cfg.partition_book = fs.RangePartitionBook(rank, P, off)
+    cfg.partition_tables = [None, x[hi:].contiguous()]
+    sess = fs.Session(1, 2, cfg)
+    req = [torch.tensor([5, -3, 0, -1, 7]), torch.tensor([-2, 4])]
+    sess.async_slice_tensors(req, rank)
+    sess.wait_slice_tensors()
+    res = sess.get_slice_tensors()
+    assert res[0][0].numel() == 0 and res[0][1].tolist() == [0, 2, 4] and res[0][2].tolist() == [1, 3]
+    assert torch.equal(res[1][0].cpu(), cfg.x_cpu[torch.tensor([4])]) and res[1][1].tolist() == [1] and res[1][2].tolist() == [0]
