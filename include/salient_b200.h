@@ -163,6 +163,8 @@ typedef struct spp_sampler_ws {
   int32_t* cand;         /* int32[cand_words] candidate slots of the fused sampled-hop path     */
                          /* (NULL: always use the general path)                                  */
   int64_t cand_words;
+  int32_t table_direct;  /* != 0: slot == node id, table_slots >= num_nodes (need not be pow2)   */
+  int32_t _pad;
 } spp_sampler_ws;
 
 typedef struct spp_sampler_sizes_t {
@@ -171,6 +173,7 @@ typedef struct spp_sampler_sizes_t {
   int64_t table_slots;
   int64_t tile_words;
   int64_t cand_words;
+  int64_t table_direct;     /* 1: use a direct-mapped table of table_slots = num_nodes entries  */
   int64_t hop_targets[SPP_MAX_HOPS]; /* bound T_h                                              */
   int64_t hop_edges[SPP_MAX_HOPS];   /* bound E_h (-1: data dependent, full neighbourhood)     */
 } spp_sampler_sizes_t;

@@ -55,12 +55,14 @@ class SamplerWs(Structure):
     _fields_ = [("table", c_void_p), ("table_slots", c_int64), ("n_ids", c_void_p),
                 ("max_nodes", c_int64), ("tgt_start", c_void_p), ("tgt_deg", c_void_p),
                 ("max_targets", c_int64), ("tile_state", c_void_p), ("tile_words", c_int64),
-                ("meta", c_void_p), ("cand", c_void_p), ("cand_words", c_int64)]
+                ("meta", c_void_p), ("cand", c_void_p), ("cand_words", c_int64),
+                ("table_direct", c_int32), ("_pad", c_int32)]
 
 
 class SamplerSizes(Structure):
     _fields_ = [("max_nodes", c_int64), ("max_targets", c_int64), ("table_slots", c_int64),
-                ("tile_words", c_int64), ("cand_words", c_int64), ("hop_targets", c_int64 * SPP_MAX_HOPS),
+                ("tile_words", c_int64), ("cand_words", c_int64), ("table_direct", c_int64),
+                ("hop_targets", c_int64 * SPP_MAX_HOPS),
                 ("hop_edges", c_int64 * SPP_MAX_HOPS)]
 
 

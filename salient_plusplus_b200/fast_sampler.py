@@ -185,6 +185,7 @@ class _Workspace:
         self.max_nodes = int(sz.max_nodes)
         self.max_targets = int(sz.max_targets)
         self.table = torch.empty(int(sz.table_slots), dtype=torch.int64, device=device)
+        self.table_direct = int(sz.table_direct)
         self.n_ids = torch.empty(self.max_nodes, dtype=torch.int32, device=device)
         self.tgt_start = torch.empty(self.max_targets, dtype=torch.int64, device=device)
         self.tgt_deg = torch.empty(self.max_targets, dtype=torch.int32, device=device)
@@ -197,7 +198,7 @@ class _Workspace:
         self.c = SamplerWs(self.table.data_ptr(), self.table.numel(), self.n_ids.data_ptr(), self.max_nodes,
                            self.tgt_start.data_ptr(), self.tgt_deg.data_ptr(), self.max_targets,
                            self.tile_state.data_ptr(), self.tile_state.numel(), self.meta.data_ptr(),
-                           self.cand.data_ptr(), self.cand.numel())
+                           self.cand.data_ptr(), self.cand.numel(), self.table_direct, 0)
 
     def ensure_tiles(self, items: int):
         words = 2 + (max(items, 1) + 1023) // 1024 + 30
@@ -684,7 +685,7 @@ class Session:
         split_words = int(self._lib.spp_split_scratch_words(self._sz.max_nodes)) if cfg.distributed else 0
         sz = self._sz
         self._pool_key = (self._device.index, int(sz.max_nodes), int(sz.max_targets), int(sz.table_slots),
-                          int(sz.tile_words), int(sz.cand_words), max_bs, split_words)
+                          int(sz.table_direct), int(sz.tile_words), int(sz.cand_words), max_bs, split_words)
         pool = _SLOT_POOL.setdefault(self._pool_key, [])
         self._slots = [pool.pop() if pool else _Slot(sz, self._device, max_bs, split_words) for _ in range(depth)]
         self._released = False

@@ -37,8 +37,8 @@ def test_struct_layouts_match_header():
     from salient_plusplus_b200 import _lib
     assert ctypes.sizeof(_lib.FeatureMap) == 4 + 4 + 17 * 8 + 16 * 8 + 8 + 8 + 16
     assert ctypes.sizeof(_lib.Graph) == 32
-    assert ctypes.sizeof(_lib.SamplerWs) == 96
-    assert ctypes.sizeof(_lib.SamplerSizes) == 5 * 8 + 2 * 8 * 8
+    assert ctypes.sizeof(_lib.SamplerWs) == 104
+    assert ctypes.sizeof(_lib.SamplerSizes) == 6 * 8 + 2 * 8 * 8
 
 
 def test_sampler_sizes_host_only(lib):
@@ -53,6 +53,9 @@ def test_sampler_sizes_host_only(lib):
     # node bound capped by the graph size, edge bound by the maximum degree
     assert lib.spp_sampler_sizes(1024, sizes, 3, 0, 100000, 7, ctypes.byref(out)) == 0
     assert out.max_nodes == 101024 and list(out.hop_edges)[:3] == [1024 * 7, 8192 * 7, 65536 * 5]
+    assert out.table_direct == 1 and out.table_slots == 100000      # small graph: direct-mapped table
+    assert lib.spp_sampler_sizes(1024, sizes, 3, 0, 111059956, 500, ctypes.byref(out)) == 0
+    assert out.table_direct == 0 and out.table_slots == 2097152     # papers100M-sized graph: hashed, L2 resident
     # with replacement every target with a neighbour emits exactly k edges: no max_degree tightening
     assert lib.spp_sampler_sizes(1024, sizes, 3, 1, 100000, 7, ctypes.byref(out)) == 0
     assert list(out.hop_edges)[:2] == [15360, 163840]
@@ -115,7 +118,7 @@ int main(void) {
   if (s.max_nodes != 1081344) return 3;
   if (spp_gather_rows(0, 0, 0, 1, 1, 0, 0, 1, 0) == 0) return 4;   /* bad row_bytes must fail */
   printf("%s\\n", spp_last_error());
-  return sizeof(spp_batch_job) == 824 ? 0 : 5;
+  return sizeof(spp_batch_job) == 832 ? 0 : 5;
 }
 ''')
     exe = tmp_path / "abi"

@@ -448,3 +448,18 @@ def test_randomized_book_cache_and_sample_adj(fs, case):
                                        rng_seed=99 + case)
         assert np.array_equal(rp.cpu().numpy(), orp) and np.array_equal(cl.cpu().numpy(), ocl)
         assert np.array_equal(n_id.cpu().numpy(), on)
+
+
+@pytest.mark.parametrize("mode", ["hash", "direct"])
+@pytest.mark.parametrize("sizes", [[15, 10, 5], [-1, -1], [40, 3], [5, -1]])
+def test_both_table_flavours(fs, monkeypatch, mode, sizes):
+    """The id table is direct-mapped for small graphs and hashed (L2 resident) for large ones;
+    both flavours must give identical, oracle-exact results (SPP_TABLE forces the choice)."""
+    monkeypatch.setenv("SPP_TABLE", mode)
+    rowptr, col = small_graph(n=4000, e=120000)
+    idx = S.seeds(rowptr.numel() - 1, 200)
+    idx[3] = idx[77]
+    n_id, adjs = fs.multilayer_sample(idx, sizes, rowptr, col, seed=4242)
+    on, oa = O.multilayer_sample(idx.numpy(), sizes, rowptr.numpy(), col.numpy(), rng_mode=O.RNG_COUNTER, rng_seed=4242)
+    assert np.array_equal(n_id.cpu().numpy(), on)
+    assert adjs_equal(adjs, oa)

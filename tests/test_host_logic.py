@@ -67,4 +67,4 @@ def test_adj_and_batches():
 
 
 def test_struct_sizes_stable():
-    assert ctypes.sizeof(_lib.BatchJob) == 824
+    assert ctypes.sizeof(_lib.BatchJob) == 832
