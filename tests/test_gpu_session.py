@@ -265,3 +265,35 @@ def test_async_slice_tensors_contract(fs, data):
     res = sess.get_slice_tensors()
     assert res[0][0].numel() == 0 and res[0][1].tolist() == [0, 2, 4] and res[0][2].tolist() == [1, 3]
     assert torch.equal(res[1][0].cpu(), cfg.x_cpu[torch.tensor([4])]) and res[1][1].tolist() == [1] and res[1][2].tolist() == [0]
+
+
+def test_remote_frequency_statistics(fs, data):
+    """cache_strategy == 'simulation' support (fast_sampler.cpp:835-880,1093-1103): how often each
+    remote vertex was needed over an epoch, most frequent first."""
+    rowptr, col, x, y, N = data
+    P, rank = 4, 1
+    off = S.equal_partition_offsets(N, P)
+    lo, hi = int(off[rank]), int(off[rank + 1])
+    idx = S.seeds(N, 256, lo=lo, hi=hi)
+    cfg = _config(fs, torch.empty((0, x.size(1)), dtype=x.dtype), y, rowptr, col, idx, distributed=True,
+                  count_remote_frequency=True, use_cache=False, sizes=[10, 5])
+    cfg.x_gpu = x[lo:hi].contiguous()
+    cfg.partition_book = fs.RangePartitionBook(rank, P, off)
+    cfg.partition_tables = [x[int(off[p]):int(off[p + 1])].contiguous() if p != rank else None for p in range(P)]
+    sess = fs.Session(1, 4, cfg)
+    want = np.zeros(N, dtype=np.int64)
+    while True:
+        b = sess.blocking_get_batch_distributed()
+        if b is None:
+            break
+        st, en = b.idx_range
+        on, _ = O.multilayer_sample(idx[st:en].numpy(), [10, 5], rowptr.numpy(), col.numpy(), rng_mode=O.RNG_COUNTER,
+                                    rng_seed=O.session_rng_seed(en))
+        remote = on[(on < lo) | (on >= hi)]
+        np.add.at(want, remote, 1)
+    sess.reduce_multithreaded_frequency_counts()
+    f, v = sess.remote_frequency_tensor.numpy(), sess.remote_vertices_ordered_by_freq.numpy()
+    assert np.all(np.diff(f) <= 0) and f.sum() == want.sum() and len(v) == np.count_nonzero(want)
+    assert np.array_equal(want[v], f)
+    top = sess.get_n_most_freq_remote_vertices(10).numpy()
+    assert np.array_equal(top, v[:10]) and want[top].min() >= np.sort(want)[-10]
