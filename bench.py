@@ -125,13 +125,13 @@ def dist_env():
     return rank, world, local
 
 
-def make_graph(shape: str, scale: float, device):
+def make_graph(shape: str, scale: float, device, locality: float = 0.0, parts: int = 8):
     from salient_plusplus_b200 import synthetic as S
     n, e, f, dt = S.SHAPES[shape]
     if shape in ("papers100M", "mag240m"):
         e //= 2  # BASELINE's 1.6B is taken as the CSR entry count ("say which")
     n, e = max(1024, int(n * scale)), max(4096, int(e * scale))
-    rowptr, col = S.powerlaw_graph(n, e, seed=1, device=device)
+    rowptr, col = S.powerlaw_graph(n, e, seed=1, device=device, locality=locality, locality_parts=parts)
     return n, f, dt, rowptr, col
 
 
@@ -217,7 +217,7 @@ def reference_arm(args):
     from salient_plusplus_b200 import synthetic as S
     shape, sizes, bs, desc = WORKLOADS[args.workload]
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    n, f, dt, rowptr, col = make_graph(shape, args.scale, dev)
+    n, f, dt, rowptr, col = make_graph(shape, args.scale, dev, args.locality, max(args.gpus, args.parts, 1))
     rowptr, col = rowptr.cpu(), col.cpu()
     x = S.features(n, f, dt, seed=2, device=dev).cpu()
     y = S.labels(n, seed=3)
@@ -263,7 +263,7 @@ def ours(args):
 
     shape, sizes, bs, desc = WORKLOADS[args.workload]
     K, W = args.steps, args.warmup
-    n, f, dt, rowptr, col = make_graph(shape, args.scale, dev)
+    n, f, dt, rowptr, col = make_graph(shape, args.scale, dev, args.locality, max(world, args.parts, 1))
     col32 = col.to(torch.int32)
     del col
     y = S.labels(n, seed=3, device=dev)
@@ -478,7 +478,8 @@ def ours(args):
             "dtype": "int64", "data": "synthetic",
             "config": {"workload": desc + (f"; features partitioned {P}-way, {args.cache_pct}% replicated "
                                            f"{args.cache_policy}-ranked cache, P2P gather over NVLink" if P > 1 else ""),
-                       "graph_generator": "Chung-Lu power law gamma=2.5 head_offset=100 seed=1, symmetrised, deduplicated",
+                       "graph_generator": "Chung-Lu power law gamma=2.5 head_offset=100 seed=1, symmetrised, deduplicated"
+                                          + (f", partition locality {args.locality}" if args.locality > 0 else ""),
                        "nnz": int(col32.numel()), "mean_nodes_per_batch": round(mean_nodes, 1),
                        "streams_in_flight": D, "scale": args.scale, "feature_partitions": P,
                        "l2": "inputs larger than L2 (feature table + CSR >> 126 MB, random rows)"},
@@ -517,6 +518,9 @@ def main():
     ap.add_argument("--cache-pct", type=float, default=15.0)
     ap.add_argument("--parts", type=int, default=0, help="feature partitions (default: one per GPU)")
     ap.add_argument("--cache-policy", default="vip", choices=["vip", "degree"])
+    ap.add_argument("--locality", type=float, default=0.0,
+                    help="probability that an edge stays inside its source's partition block (0 = locality-free "
+                         "Chung-Lu graph, the worst case for range-partitioned features)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile the public-API loop (stderr)")
     args = ap.parse_args()

@@ -30,8 +30,15 @@ SHAPES = {
 
 def powerlaw_graph(num_nodes: int, num_directed_edges: int, *, gamma: float = 2.5,
                    head_offset: float = 100.0, seed: int = 1, device="cpu",
-                   symmetrize: bool = True, chunk: int = 1 << 27) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Returns ``(rowptr int64[N+1], col int64[nnz])`` with ascending columns in each row."""
+                   symmetrize: bool = True, chunk: int = 1 << 27, locality: float = 0.0,
+                   locality_parts: int = 8) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns ``(rowptr int64[N+1], col int64[nnz])`` with ascending columns in each row.
+
+    ``locality`` > 0 plants partition structure: with that probability the destination of a
+    directed edge is folded into the source's block of the ``locality_parts`` equal id ranges
+    (what a METIS partition followed by the reference's contiguous relabelling gives,
+    driver/dataset.py:309-323).  0 (default) is the locality-free worst case for range-partitioned
+    features."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -52,6 +59,12 @@ def powerlaw_graph(num_nodes: int, num_directed_edges: int, *, gamma: float = 2.
         del u
         src = relabel[src]
         dst = relabel[dst]
+        if locality > 0.0:
+            bsz = (num_nodes + locality_parts - 1) // locality_parts
+            fold = torch.rand(m, generator=g, device=dev) < locality
+            blk = torch.div(src, bsz, rounding_mode="floor")
+            folded = (blk * bsz + dst % bsz).clamp_(max=num_nodes - 1)
+            dst = torch.where(fold, folded, dst)
         keep = src != dst
         src, dst = src[keep], dst[keep]
         keys.append(src * num_nodes + dst)
