@@ -457,6 +457,43 @@ def ours(args):
         ms, t_e2e = t.tolist()
     assert got == K
 
+    # ---- NVLink roofline (N > 1): the P2P miss fetch alone, every row owned by a peer ------------
+    nvlink = None
+    if world > 1:
+        import ctypes as _ct
+        rows_n = 1_000_000
+        gq = torch.Generator(device=dev).manual_seed(99 + rank)
+        owner = (rank + 1 + torch.randint(0, P - 1, (rows_n,), generator=gq, device=dev)) % P
+        offd = off.to(dev)
+        span = (offd[1:] - offd[:-1])[owner]
+        r = (torch.rand(rows_n, generator=gq, device=dev, dtype=torch.float64) * span.double()).long()
+        ids = (offd[owner] + torch.minimum(r, span - 1).clamp_(min=0)).to(torch.int64)
+        fm_nc = fs.make_feature_map(off.tolist(), rank, tables, None, None, ptrs, ltab.pitch, 0)  # no cache
+        outb = torch.empty((rows_n, f), dtype=dt, device=dev)
+        spn = main.cuda_stream
+        for _ in range(3):
+            _lib.check(lib.spp_gather_partitioned(_ct.byref(fm_nc), row_bytes, ids.data_ptr(), 1, rows_n, None,
+                                                  outb.data_ptr(), rows_n, None, spn))
+        barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        n0.record(main)
+        for _ in range(reps):
+            _lib.check(lib.spp_gather_partitioned(_ct.byref(fm_nc), row_bytes, ids.data_ptr(), 1, rows_n, None,
+                                                  outb.data_ptr(), rows_n, None, spn))
+        n1.record(main)
+        torch.cuda.synchronize()
+        nv_ms = n0.elapsed_time(n1) / reps
+        tms = torch.tensor([nv_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        nv_ms = float(tms.item())
+        gbs = rows_n * row_bytes / (nv_ms * 1e-3) / 1e9
+        nvlink = {"bound": "nvlink", "kernel": "k_gather partitioned, all rows on peers (P2P miss fetch)",
+                  "achieved": round(gbs, 1), "peak": 900.0, "unit": "GB/s inbound per GPU", "frac": round(gbs / 900.0, 4),
+                  "measured_peer_copy_peak": 770.0, "frac_of_measured": round(gbs / 770.0, 4),
+                  "rows": rows_n, "row_bytes": row_bytes, "ms": round(nv_ms, 4), "timing": "CUDA events, max over ranks"}
+        del outb, ids
+
     # ---- CPU baseline beside it (rank 0, N = 1): the reference fast_sampler on the host cores --
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -496,8 +533,11 @@ def ours(args):
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "avg_launch_ms": round(g_ms_avg, 5),
                          "algorithmic_bytes_per_launch": int(alg_bytes_per_launch),
-                         "bytes_model": "N_b * (2*row_bytes + 4)", "launches_timed": len(evs)},
+                         "bytes_model": "N_b * (2*row_bytes + 4)", "launches_timed": len(evs),
+                         "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)},
         }
+        if nvlink is not None:
+            line["nvlink_roofline"] = nvlink
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

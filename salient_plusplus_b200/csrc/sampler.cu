@@ -2,23 +2,22 @@
 // global->local relabelling.  Replaces sample_adj (fast_sampler/sample_cpu.hpp:25-143) and
 // multilayer_sample (fast_sampler/fast_sampler.cpp:191-236) of the reference.
 //
-// Per hop h (frontier = every node discovered so far, T of them; fan-out k):
-//   1. k_hop_count_scan   degree -> kept-edge count per target, single-pass decoupled look-back
-//                         scan -> out_rowptr (int64[T+1]); caches rowptr[n]/deg per target.
-//   2. k_hop_sample       a group of G lanes per target chooses the neighbours (all of them, k draws
-//                         with replacement, or Floyd's algorithm with a counter-based RNG), reads
-//                         col[], inserts the global id into the L2-resident hash table and
-//                         atomicMax-es ~(T + p) into the entry, p = global candidate position.
-//                         Established nodes hold ~local with local < T, so they always win;
-//                         a new node ends up holding the SMALLEST candidate position that saw it.
-//   3. k_hop_compact      order-preserving compaction (look-back scan) of the candidates that
-//                         own their entry (entry == ~(T + p)): the r-th such candidate defines
-//                         local id T + r.  This is exactly the sequential first-discovery order of
-//                         the reference (seeds, then row by row, neighbour by neighbour).
-//   4. k_relabel_sort_*   every row: candidate slot -> local id, ascending sort inside the row
-//                         (std::sort at sample_cpu.hpp:126), int64 output.
+// Common idea of both code paths below.  Per hop h the frontier is every node discovered so far
+// (T of them); a candidate edge gets a position p in the reference's sequential visiting order
+// (target by target, neighbour by neighbour).  The global id of every candidate is inserted into
+// an L2-resident id table and ~(T + p) is atomicMax-ed into its entry: established nodes hold
+// ~local with local < T so they always win, a new node ends up holding the SMALLEST position that
+// saw it.  An order-preserving compaction of the candidates that own their entry then hands out
+// local ids T, T+1, ... in exactly the reference's first-discovery order, and a last pass turns
+// candidate slots into local ids and sorts every row ascending (std::sort, sample_cpu.hpp:126).
 //
-// Hash entry: 64 bits = { key + 1 , ~local } ; empty = 0, so the table is cleared by a memset.
+//   General path (full neighbourhood k < 0, with replacement, fan-out > 32), 4-5 kernels per hop:
+//     k_hop_count_scan -> k_hop_sample<mode,G,PPL> -> k_hop_compact -> k_relabel_sort_general
+//     (-> k_sort_large_rows); 64-bit decoupled look-back scans, data-dependent edge counts.
+//   Fused path (1 <= k <= 32, without replacement: every reference configuration), 3 kernels per hop:
+//     k_hop_sample_fused -> k_hop_compact_fused -> k_relabel_sort_fused; see the banner further down.
+//
+// Table entry: 64 bits = { key + 1 , ~local } ; empty = 0, so the table is cleared by a memset.
 #include <atomic>
 #include <cstdlib>
 
