@@ -369,6 +369,19 @@ def ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(lib.spp_launch_count() - launches0)
+    if args.device_only:
+        clocks.stop()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if rank == 0:
+            print(json.dumps({"device_only": True, "batches_per_s": round(world * K / (ms * 1e-3), 1),
+                              "us_per_batch": round(1000.0 * ms / K, 2), "launches": launches,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("SPP_")}}), flush=True)
+        if world > 1:
+            dist.barrier()
+        return
 
     # ---- roofline pass: the feature gather timed with CUDA events on its own stream -----------
     evs = run_batches(W, min(K, 64), time_gather=True, single_stream=True)
@@ -562,6 +575,8 @@ def main():
                     help="probability that an edge stays inside its source's partition block (0 = locality-free "
                          "Chung-Lu graph, the worst case for range-partitioned features)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true",
+                    help="A/B experiments: print the device-timed batches/s and exit (not a bench line)")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile the public-API loop (stderr)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -224,6 +224,16 @@ int spp_sample_hop_fill(const spp_graph* graph_host, int hop, int32_t fanout, in
  * fused compaction kernel's phases (tools/compact_timeline.py); NULL switches it off */
 void spp_debug_set_timeline(void* dev_ptr);
 
+/* diagnostics: event trace of the launch sequence.  begin(max_marks) arms it (0 disarms); every
+ * kernel / copy issued by the library is then followed by a timing event on its stream.  end()
+ * synchronises the device and returns the marks in issue order: label (0 batch begin, 1 seeds
+ * H2D, 2 table clear, 3 seeds init, 4 sample, 5 compact, 6 relabel+sort, 7 export n_id, 8 owner
+ * split, 9 feature gather, 10 label gather, 11 meta D2H, 12 join), hop, stream handle and
+ * milliseconds since the first mark (tools/trace_pipeline.py). */
+int spp_trace_begin(int64_t max_marks);
+int64_t spp_trace_end(int32_t* labels_host, int32_t* hops_host, uint64_t* streams_host,
+                      double* ms_host, int64_t cap);
+
 /* n_id_out[i] = (int64) ws->n_ids[i], i < meta[NODES(hop)]  (or int32 copy if out_is_64 == 0) */
 int spp_sample_export_nids(const spp_sampler_ws* ws_host, int hop, void* n_id_out, int out_is_64,
                            int64_t max_nodes, void* stream);

@@ -31,6 +31,7 @@ EXPORTED = [
     "spp_split_scratch_words", "spp_split_by_owner",
     "spp_sampler_sizes", "spp_sample_minibatch", "spp_sample_begin", "spp_sample_hop_count",
     "spp_sample_hop_fill", "spp_sample_export_nids", "spp_debug_set_timeline",
+    "spp_trace_begin", "spp_trace_end",
     "spp_batch_enqueue", "spp_executor_create", "spp_executor_destroy", "spp_executor_submit",
     "spp_executor_poll", "spp_executor_wait", "spp_executor_times",
     "spp_vip_hop",
@@ -133,6 +134,9 @@ def load() -> ctypes.CDLL:
     L.spp_debug_set_timeline.restype = None
     L.spp_debug_set_timeline.argtypes = [vp]
     L.spp_sample_export_nids.argtypes = [POINTER(SamplerWs), ci, vp, ci, i64, vp]
+    L.spp_trace_begin.argtypes = [i64]
+    L.spp_trace_end.restype = i64
+    L.spp_trace_end.argtypes = [POINTER(i32), POINTER(i32), POINTER(c_uint64), POINTER(ctypes.c_double), i64]
     L.spp_batch_enqueue.argtypes = [POINTER(BatchJob)]
     L.spp_executor_create.restype = vp
     L.spp_executor_create.argtypes = [ci]
@@ -162,6 +166,23 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().spp_last_error().decode("utf-8", "replace")
         raise SalientB200Error(f"{what or 'libsalient_b200'} failed (code {rc}): {msg}")
+
+
+TRACE_LABELS = ["batch_begin", "seeds_h2d", "table_clear", "seeds_init", "sample", "compact", "relabel_sort",
+                "export_nid", "owner_split", "feature_gather", "label_gather", "meta_d2h", "join"]
+
+
+def trace_begin(max_marks: int = 4096) -> None:
+    """Arm the library's event trace (diagnostics; tools/trace_pipeline.py)."""
+    check(load().spp_trace_begin(int(max_marks)), "spp_trace_begin")
+
+
+def trace_end(cap: int = 4096):
+    """Stop the trace; returns [(label, hop, stream handle, ms since the first mark)] in issue order."""
+    lab, hop = (c_int32 * cap)(), (c_int32 * cap)()
+    st, ms = (c_uint64 * cap)(), (ctypes.c_double * cap)()
+    n = int(load().spp_trace_end(lab, hop, st, ms, cap))
+    return [(TRACE_LABELS[lab[i]], int(hop[i]), int(st[i]), float(ms[i])) for i in range(n)]
 
 
 def launch_count() -> int:

@@ -21,7 +21,7 @@ except Exception:  # noqa: BLE001
         def __init__(self, rowptr=None, row=None, col=None, value=None, sparse_sizes=None, is_sorted=False,
                      trust_data=False):
             self._rowptr, self._row, self._col, self._value = rowptr, row, col, value
-            self._sparse_sizes = tuple(int(v) for v in sparse_sizes)
+            self._sparse_sizes = (int(sparse_sizes[0]), int(sparse_sizes[1]))
 
         def csr(self):
             return self._rowptr, self._col, self._value
@@ -85,4 +85,4 @@ def Adj__from_fast_sampler(adj) -> Adj:
     """fast_trainer/samplers.py:22-30"""
     rowptr, col, e_id, sparse_sizes = adj
     return Adj(SparseTensor(rowptr=rowptr, row=None, col=col, value=None, sparse_sizes=tuple(sparse_sizes),
-                            is_sorted=True, trust_data=True), e_id, tuple(sparse_sizes)[::-1])
+                            is_sorted=True, trust_data=True), e_id, (sparse_sizes[1], sparse_sizes[0]))

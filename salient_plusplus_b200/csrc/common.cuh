@@ -14,6 +14,33 @@ int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 int num_sms();
 
+// diagnostics (runtime.cu): event mark on `st` after an operation was issued; no-op unless a
+// trace is active (spp_trace_begin)
+enum TraceLabel {
+  kTrBatchBegin = 0, kTrSeedsH2D, kTrTableClear, kTrSeedsInit, kTrSample, kTrCompact, kTrRelabel,
+  kTrExport, kTrSplit, kTrGather, kTrLabels, kTrMetaD2H, kTrJoin
+};
+void trace_mark(int label, int hop, cudaStream_t st);
+
+// Side streams of a mini-batch's main stream (runtime.cu; created on first use, one set per main
+// stream): the relabel/sort kernels of the sampled hops and, optionally, the feature gather are
+// forked onto them so that they stay off the sampler's dependent kernel chain.
+struct AuxStreams {
+  cudaStream_t relabel, gather;
+  cudaEvent_t fork[SPP_MAX_HOPS], fork_gather, join_relabel, join_gather;
+};
+AuxStreams* aux_streams(cudaStream_t main);
+// bit 0: relabel/sort kernels on the side stream; bit 1: feature + label gather on a side stream
+// (SPP_FORK overrides the default)
+int pipeline_flags();
+
+// sampler.cu
+int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batch_size, const int32_t* sizes,
+                          int n_hops, int replace, uint64_t rng_seed, const spp_sampler_ws* ws,
+                          int64_t* const* out_rowptr, int64_t* const* out_col, const int64_t* out_col_cap,
+                          int64_t* n_id_out, cudaStream_t st, bool* pending);
+int join_relabel(cudaStream_t st, bool pending);
+
 #define SPP_CUDA(expr)                                        \
   do {                                                        \
     cudaError_t _e = (expr);                                  \

@@ -2,7 +2,10 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -38,9 +41,106 @@ int num_sms() {
   return sms[dev];
 }
 
+// ---- diagnostics: event trace of the launch sequence ------------------------------------------
+// A mark is a timing-enabled CUDA event recorded on the launching stream right after a kernel
+// (or copy) was issued; the time between consecutive marks of one stream is that operation's
+// duration as the stream saw it, i.e. including the time it waited for SM slots while other
+// in-flight mini-batches were running (tools/trace_pipeline.py).
+struct TraceMark {
+  int label;
+  int hop;
+  cudaStream_t stream;
+  cudaEvent_t ev;
+};
+static std::atomic<int> g_trace_on{0};
+static std::mutex g_trace_mu;
+static std::vector<TraceMark> g_trace;
+static size_t g_trace_cap = 0;
+
+void trace_mark(int label, int hop, cudaStream_t st) {
+  if (!g_trace_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  if (g_trace.size() >= g_trace_cap) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  g_trace.push_back({label, hop, st, ev});
+}
+
+// ---- side streams ----------------------------------------------------------------------------
+static std::mutex g_aux_mu;
+static std::vector<std::pair<cudaStream_t, AuxStreams*>> g_aux;
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
+int pipeline_flags() {
+  static int v = -1;
+  if (v < 0) v = env_int("SPP_FORK", 0) & 3;
+  return v;
+}
+
+AuxStreams* aux_streams(cudaStream_t main) {
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  for (auto& e : g_aux)
+    if (e.first == main) return e.second;
+  // stream priorities: numerically lower = scheduled first; 0 is the default (and lowest)
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  auto clampp = [&](int p) { return p > lo ? lo : (p < hi ? hi : p); };
+  auto* a = new AuxStreams();
+  bool ok = cudaStreamCreateWithPriority(&a->relabel, cudaStreamNonBlocking, clampp(env_int("SPP_RELABEL_PRIO", 0))) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&a->gather, cudaStreamNonBlocking, clampp(env_int("SPP_GATHER_PRIO", 0))) == cudaSuccess;
+  for (int h = 0; ok && h < SPP_MAX_HOPS; ++h) ok = cudaEventCreateWithFlags(&a->fork[h], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&a->fork_gather, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&a->join_relabel, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&a->join_gather, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    cuda_fail(cudaGetLastError(), "side stream creation");
+    delete a;
+    return nullptr;
+  }
+  g_aux.emplace_back(main, a);
+  return a;
+}
+
 }  // namespace spp
 
 extern "C" {
+
+int spp_trace_begin(int64_t max_marks) {
+  std::lock_guard<std::mutex> lk(spp::g_trace_mu);
+  for (auto& m : spp::g_trace) cudaEventDestroy(m.ev);
+  spp::g_trace.clear();
+  spp::g_trace_cap = max_marks > 0 ? (size_t)max_marks : 0;
+  spp::g_trace.reserve(spp::g_trace_cap);
+  spp::g_trace_on.store(max_marks > 0 ? 1 : 0);
+  return 0;
+}
+
+int64_t spp_trace_end(int32_t* labels, int32_t* hops, uint64_t* streams, double* ms, int64_t cap) {
+  spp::g_trace_on.store(0);
+  std::lock_guard<std::mutex> lk(spp::g_trace_mu);
+  cudaDeviceSynchronize();
+  int64_t n = 0;
+  for (auto& m : spp::g_trace) {
+    if (n < cap && labels && hops && streams && ms) {
+      float f = 0.f;
+      cudaEventElapsedTime(&f, spp::g_trace[0].ev, m.ev);
+      labels[n] = m.label;
+      hops[n] = m.hop;
+      streams[n] = (uint64_t)(uintptr_t)m.stream;
+      ms[n] = (double)f;
+      ++n;
+    }
+  }
+  for (auto& m : spp::g_trace) cudaEventDestroy(m.ev);
+  spp::g_trace.clear();
+  cudaGetLastError();
+  return n;
+}
 
 int spp_abi_version(void) { return SPP_ABI_VERSION; }
 const char* spp_last_error(void) { return spp::g_err; }

@@ -976,8 +976,10 @@ static int launch_begin(const spp_graph* g, const int64_t* seeds, int64_t bs, co
                                                  (long long)bs, (long long)ws->max_nodes);
   if (bs > 0 && !seeds) return fail(SPP_EINVAL, "sampler: null seeds");
   SPP_CUDA(cudaMemsetAsync(ws->table, 0, (size_t)ws->table_slots * sizeof(uint64_t), st));
+  trace_mark(kTrTableClear, 0, st);
   k_seeds_init<<<1, 1024, 0, st>>>(seeds, bs, ws->n_ids, make_table(ws), ws->meta);
   SPP_KERNEL_CHECK("k_seeds_init");
+  trace_mark(kTrSeedsInit, 0, st);
   return 0;
 }
 
@@ -1076,22 +1078,27 @@ static bool fused_ok(int32_t fanout, int replace, const spp_sampler_ws* ws) {
 }
 
 // one sampled hop through the fused path (no host synchronisation, no memset)
+// `cand_off`: this hop's first word inside ws->cand (every hop of a mini-batch has its own range,
+// so a hop's relabel/sort kernel may still be reading its candidates while the next hop samples).
+// `relabel_st`: stream of the relabel/sort kernel; when it differs from `st` the kernel is forked
+// off behind `fork_ev` and the caller joins later (see sample_minibatch_impl).
 static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_t rng_seed, int64_t max_targets,
                             int64_t max_edges, const spp_sampler_ws* ws, int64_t* out_rowptr, int64_t* out_col,
-                            cudaStream_t st) {
+                            cudaStream_t st, int64_t cand_off = 0, cudaStream_t relabel_st = nullptr,
+                            cudaEvent_t fork_ev = nullptr) {
   if (hop < 0 || hop >= SPP_MAX_HOPS) return fail(SPP_EINVAL, "sampler: hop %d out of range", hop);
   if (!out_rowptr || (!out_col && max_edges > 0)) return fail(SPP_EINVAL, "sampler: null output");
   FusedParams fp{};
   fp.h = make_params(g, ws, hop, fanout, 0, rng_seed, max_targets, max_edges, out_rowptr, out_col);
   const int64_t vmax = fp.h.max_targets * (int64_t)fanout;
-  if (vmax > ws->cand_words)
-    return fail(SPP_ECAPACITY, "sampler: cand buffer too small (%lld needed, %lld given)", (long long)vmax,
-                (long long)ws->cand_words);
+  if (cand_off < 0 || (cand_off & 7) || cand_off + vmax > ws->cand_words)
+    return fail(SPP_ECAPACITY, "sampler: cand buffer too small (%lld needed, %lld given)",
+                (long long)(cand_off + vmax), (long long)ws->cand_words);
   const int64_t tiles = ceil_div(vmax > 0 ? vmax : 1, kFusedTile);
   if (2 + tiles > ws->tile_words)
     return fail(SPP_ECAPACITY, "sampler: tile_state too small (%lld words needed)", (long long)(2 + tiles));
-  fp.cand = reinterpret_cast<uint32_t*>(ws->cand);
-  fp.cand_cap = ws->cand_words;
+  fp.cand = reinterpret_cast<uint32_t*>(ws->cand) + cand_off;
+  fp.cand_cap = ws->cand_words - cand_off;
   fp.timeline = g_timeline.load(std::memory_order_relaxed);
   // epochs stay in [1, 2^30): they can never equal the high word of a look-back state
   // (status << 30) left behind in the shared aggregate area by the general path
@@ -1120,16 +1127,25 @@ static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_
   int64_t ctas = ceil_div(warps, kSampleThreads / 32);
   const int grid = (int)(ctas < cap ? ctas : cap);
   SPP_KERNEL_CHECK("k_hop_sample_fused");
+  trace_mark(kTrSample, hop, st);
   const int64_t scap = (int64_t)sms * 6;
   k_hop_compact_fused<<<(int)(tiles < scap ? tiles : scap), kScanThreads, 0, st>>>(fp);
   SPP_KERNEL_CHECK("k_hop_compact_fused");
+  trace_mark(kTrCompact, hop, st);
+  cudaStream_t rst = st;
+  if (relabel_st != nullptr && relabel_st != st) {
+    SPP_CUDA(cudaEventRecord(fork_ev, st));
+    SPP_CUDA(cudaStreamWaitEvent(relabel_st, fork_ev, 0));
+    rst = relabel_st;
+  }
   switch (G) {
-    case 4: k_relabel_sort_fused<4><<<grid, kSampleThreads, 0, st>>>(fp); break;
-    case 8: k_relabel_sort_fused<8><<<grid, kSampleThreads, 0, st>>>(fp); break;
-    case 16: k_relabel_sort_fused<16><<<grid, kSampleThreads, 0, st>>>(fp); break;
-    default: k_relabel_sort_fused<32><<<grid, kSampleThreads, 0, st>>>(fp); break;
+    case 4: k_relabel_sort_fused<4><<<grid, kSampleThreads, 0, rst>>>(fp); break;
+    case 8: k_relabel_sort_fused<8><<<grid, kSampleThreads, 0, rst>>>(fp); break;
+    case 16: k_relabel_sort_fused<16><<<grid, kSampleThreads, 0, rst>>>(fp); break;
+    default: k_relabel_sort_fused<32><<<grid, kSampleThreads, 0, rst>>>(fp); break;
   }
   SPP_KERNEL_CHECK("k_relabel_sort_fused");
+  trace_mark(kTrRelabel, hop, rst);
   return 0;
 }
 
@@ -1143,6 +1159,71 @@ static int launch_export(const spp_sampler_ws* ws, int word, void* out, int out_
   if (out_is_64) k_export_nids<int64_t><<<grid, 256, 0, st>>>(ws->n_ids, ws->meta, word, cap, (int64_t*)out);
   else k_export_nids<int32_t><<<grid, 256, 0, st>>>(ws->n_ids, ws->meta, word, cap, (int32_t*)out);
   SPP_KERNEL_CHECK("k_export_nids");
+  return 0;
+}
+
+// All hops of one mini-batch.  With the relabel fork on (pipeline_flags() & 1) the relabel/sort
+// kernel of every fused hop runs on the main stream's side stream: it only reads table entries
+// that its own hop's compaction finalised (the next hop's sampler never lowers the value of an
+// established entry and only adds new slots) and its own range of `cand`, and nothing on the
+// critical path (next hop, owner split, feature gather) reads out_col.  *pending tells the caller
+// that join_relabel() must be called on `st` before the batch is complete.
+int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batch_size, const int32_t* sizes,
+                          int n_hops, int replace, uint64_t rng_seed, const spp_sampler_ws* ws,
+                          int64_t* const* out_rowptr, int64_t* const* out_col, const int64_t* out_col_cap,
+                          int64_t* n_id_out, cudaStream_t st, bool* pending) {
+  *pending = false;
+  if (n_hops < 0 || n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_sample_minibatch: n_hops out of range");
+  if (n_hops > 0 && (!sizes || !out_rowptr || !out_col || !out_col_cap))
+    return fail(SPP_EINVAL, "spp_sample_minibatch: null argument");
+  if (int r = launch_begin(g, seeds, batch_size, ws, st)) return r;
+  // one range of ws->cand per fused hop when they all fit (workspaces sized by spp_sampler_sizes
+  // do); otherwise every hop reuses the start of the buffer and nothing is forked
+  int64_t need = 0, T = batch_size;
+  for (int h = 0; h < n_hops; ++h) {
+    const int64_t Tb = T < ws->max_targets ? T : ws->max_targets;
+    if (fused_ok(sizes[h], replace, ws)) need += (Tb * (int64_t)sizes[h] + 7) & ~7ll;
+    const int64_t next = T + out_col_cap[h];
+    T = next < ws->max_nodes ? next : ws->max_nodes;
+  }
+  const bool ranges = ws->cand != nullptr && need <= ws->cand_words;
+  AuxStreams* aux = (ranges && (pipeline_flags() & 1)) ? aux_streams(st) : nullptr;
+  // host-side frontier bounds (the device clamps to them and raises SPP_META_OVERFLOW)
+  int64_t cand_off = 0;
+  T = batch_size;
+  for (int h = 0; h < n_hops; ++h) {
+    int64_t Tb = T < ws->max_targets ? T : ws->max_targets;
+    if (fused_ok(sizes[h], replace, ws)) {
+      if (int r = launch_hop_fused(g, h, sizes[h], rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st,
+                                   cand_off, aux ? aux->relabel : nullptr, aux ? aux->fork[h] : nullptr))
+        return r;
+      if (aux) *pending = true;
+      if (ranges) cand_off += (Tb * (int64_t)sizes[h] + 7) & ~7ll;
+    } else {
+      // the general path rewrites table entries wholesale: earlier relabels must have finished
+      if (int r = join_relabel(st, *pending)) return r;
+      *pending = false;
+      if (int r = launch_count(g, h, sizes[h], replace, Tb, ws, out_rowptr[h], st)) return r;
+      if (int r = launch_fill(g, h, sizes[h], replace, rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st))
+        return r;
+    }
+    int64_t next = T + out_col_cap[h];
+    T = next < ws->max_nodes ? next : ws->max_nodes;
+  }
+  if (n_id_out) {
+    if (int r = launch_export(ws, SPP_META_NODES(n_hops), n_id_out, 1, ws->max_nodes, st)) return r;
+    trace_mark(kTrExport, 0, st);
+  }
+  return 0;
+}
+
+int join_relabel(cudaStream_t st, bool pending) {
+  if (!pending) return 0;
+  AuxStreams* aux = aux_streams(st);
+  if (!aux) return fail(SPP_EINVAL, "sampler: side stream missing at join");
+  SPP_CUDA(cudaEventRecord(aux->join_relabel, aux->relabel));
+  SPP_CUDA(cudaStreamWaitEvent(st, aux->join_relabel, 0));
+  trace_mark(kTrJoin, 0, st);
   return 0;
 }
 
@@ -1197,9 +1278,9 @@ int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes, int n_hops, int 
   }
   int64_t items = maxE > maxT ? maxE : maxT;
   out->tile_words = 2 + ceil_div(items > 0 ? items : 1, kScanTile) + 30;
-  int64_t cw = 0;  // fused path: virtual candidates of a sampled hop
+  int64_t cw = 0;  // fused path: virtual candidates of every sampled hop (one range per hop)
   for (int h = 0; h < n_hops; ++h)
-    if (sizes[h] >= 1 && sizes[h] <= 32 && out->hop_targets[h] * (int64_t)sizes[h] > cw) cw = out->hop_targets[h] * (int64_t)sizes[h];
+    if (sizes[h] >= 1 && sizes[h] <= 32) cw += (out->hop_targets[h] * (int64_t)sizes[h] + 7) & ~7ll;
   out->cand_words = cw + 16;
   return 0;
 }
@@ -1234,29 +1315,11 @@ int spp_sample_minibatch(const spp_graph* g, const int64_t* seeds, int64_t batch
                          int n_hops, int replace, uint64_t rng_seed, const spp_sampler_ws* ws,
                          int64_t* const* out_rowptr, int64_t* const* out_col, const int64_t* out_col_cap,
                          int64_t* n_id_out, void* stream) {
-  using namespace spp;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (n_hops < 0 || n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_sample_minibatch: n_hops out of range");
-  if (n_hops > 0 && (!sizes || !out_rowptr || !out_col || !out_col_cap))
-    return fail(SPP_EINVAL, "spp_sample_minibatch: null argument");
-  if (int r = launch_begin(g, seeds, batch_size, ws, st)) return r;
-  // host-side frontier bounds (the device clamps to them and raises SPP_META_OVERFLOW)
-  int64_t T = batch_size;
-  for (int h = 0; h < n_hops; ++h) {
-    int64_t Tb = T < ws->max_targets ? T : ws->max_targets;
-    if (fused_ok(sizes[h], replace, ws)) {
-      if (int r = launch_hop_fused(g, h, sizes[h], rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st))
-        return r;
-    } else {
-      if (int r = launch_count(g, h, sizes[h], replace, Tb, ws, out_rowptr[h], st)) return r;
-      if (int r = launch_fill(g, h, sizes[h], replace, rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st))
-        return r;
-    }
-    int64_t next = T + out_col_cap[h];
-    T = next < ws->max_nodes ? next : ws->max_nodes;
-  }
-  if (n_id_out) return launch_export(ws, SPP_META_NODES(n_hops), n_id_out, 1, ws->max_nodes, st);
-  return 0;
+  bool pending = false;
+  if (int r = spp::sample_minibatch_impl(g, seeds, batch_size, sizes, n_hops, replace, rng_seed, ws, out_rowptr, out_col,
+                                         out_col_cap, n_id_out, (cudaStream_t)stream, &pending))
+    return r;
+  return spp::join_relabel((cudaStream_t)stream, pending);
 }
 
 }  // extern "C"

@@ -23,36 +23,62 @@ extern "C" int spp_batch_enqueue(const spp_batch_job* j) {
   cudaStream_t st = (cudaStream_t)j->stream;
   if (j->n_hops < 0 || j->n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_batch_enqueue: n_hops out of range");
   const int64_t bs = j->batch_size;
+  trace_mark(kTrBatchBegin, 0, st);
   if (j->seeds_host && bs > 0) {
     if (!j->seeds_dev) return fail(SPP_EINVAL, "spp_batch_enqueue: seeds_dev missing");
     SPP_CUDA(cudaMemcpyAsync(j->seeds_dev, j->seeds_host, (size_t)bs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    trace_mark(kTrSeedsH2D, 0, st);
   }
-  if (int r = spp_sample_minibatch(&j->graph, j->seeds_dev, bs, j->sizes, j->n_hops, j->replace, j->rng_seed, &j->ws,
-                                   j->out_rowptr, j->out_col, j->out_col_cap, j->n_id_out, st))
+  // the relabel/sort kernels may be left running on the side stream: nothing below reads out_col,
+  // the join happens before the size block goes back to the host
+  bool relabel_pending = false;
+  if (int r = sample_minibatch_impl(&j->graph, j->seeds_dev, bs, j->sizes, j->n_hops, j->replace, j->rng_seed, &j->ws,
+                                    j->out_rowptr, j->out_col, j->out_col_cap, j->n_id_out, st, &relabel_pending))
     return r;
   const int64_t* n_dev = j->ws.meta + SPP_META_NODES(j->n_hops);
+  // optional: the feature + label gather on its own (lower-priority) stream
+  cudaStream_t gst = st;
+  AuxStreams* aux = nullptr;
+  if ((pipeline_flags() & 2) && (j->feature_mode || (j->y_table && bs > 0))) {
+    aux = aux_streams(st);
+    if (aux) {
+      SPP_CUDA(cudaEventRecord(aux->fork_gather, st));
+      SPP_CUDA(cudaStreamWaitEvent(aux->gather, aux->fork_gather, 0));
+      gst = aux->gather;
+    }
+  }
   if (j->do_split) {
     if (int r = spp_split_by_owner(&j->fmap, j->use_cache, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->bucket_ids,
                                    j->perm, j->bucket_counts, j->split_scratch, st))
       return r;
+    trace_mark(kTrSplit, 0, st);
   }
   if (j->feature_mode == 1) {
     if (int r = spp_gather_rows_pitched(j->table, j->table_pitch, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev,
-                                        j->x_out, j->ws.max_nodes, st))
+                                        j->x_out, j->ws.max_nodes, gst))
       return r;
+    trace_mark(kTrGather, 0, gst);
   } else if (j->feature_mode == 2) {
     if (int r = spp_gather_partitioned(&j->fmap, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->x_out,
-                                       j->ws.max_nodes, nullptr, st))
+                                       j->ws.max_nodes, nullptr, gst))
       return r;
+    trace_mark(kTrGather, 0, gst);
   }
   if (j->y_table && bs > 0) {
-    if (int r = spp_gather_rows(j->y_table, j->y_row_bytes, j->seeds_dev, 1, bs, nullptr, j->y_out, bs, st)) return r;
+    if (int r = spp_gather_rows(j->y_table, j->y_row_bytes, j->seeds_dev, 1, bs, nullptr, j->y_out, bs, gst)) return r;
+    trace_mark(kTrLabels, 0, gst);
   }
+  if (gst != st) {
+    SPP_CUDA(cudaEventRecord(aux->join_gather, gst));
+    SPP_CUDA(cudaStreamWaitEvent(st, aux->join_gather, 0));
+  }
+  if (int r = join_relabel(st, relabel_pending)) return r;
   if (j->meta_host) {
     SPP_CUDA(cudaMemcpyAsync(j->meta_host, j->ws.meta, SPP_META_WORDS * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (j->do_split)
       SPP_CUDA(cudaMemcpyAsync(j->meta_host + SPP_META_WORDS, j->bucket_counts, (SPP_MAX_PARTS + 2) * sizeof(int64_t),
                                cudaMemcpyDeviceToHost, st));
+    trace_mark(kTrMetaD2H, 0, st);
   }
   return 0;
 }

@@ -51,6 +51,33 @@ def _stream_ptr(stream: Optional[torch.cuda.Stream] = None) -> int:
     return (stream or torch.cuda.current_stream()).cuda_stream
 
 
+# Per-batch host work runs on the consumer's thread, so its cost bounds the public-API rate once
+# the GPU needs < 100 us per batch.  ``torch.cuda.stream(...)`` costs ~15 us per use (two Stream
+# objects + device-index normalisation); the raw (stream_id, device_index, device_type) triples
+# torch itself passes to its C layer are switched directly instead.
+_get_stream_raw = getattr(torch._C, "_cuda_getCurrentStream", None)
+_set_stream_raw = getattr(torch._C, "_cuda_setStream", None)
+_FAST_STREAMS = _get_stream_raw is not None and _set_stream_raw is not None
+_STREAM_OBJS: dict = {}
+
+
+def current_stream_cached(device_index: int) -> torch.cuda.Stream:
+    """``torch.cuda.current_stream(device)`` without building a new Stream object every call."""
+    if not _FAST_STREAMS:
+        return torch.cuda.current_stream(device_index)
+    raw = _get_stream_raw(device_index)
+    st = _STREAM_OBJS.get(raw)
+    if st is None:
+        st = _STREAM_OBJS[raw] = torch.cuda.Stream(stream_id=raw[0], device_index=raw[1], device_type=raw[2])
+    return st
+
+
+class OwnedSample(tuple):
+    """The tuple a non-distributed Session returns, plus ``owners``: the distinct allocations its
+    tensors are views of (``record_stream`` on those covers every view)."""
+    owners: tuple = ()
+
+
 _RESIDENT: "OrderedDict[tuple, tuple]" = OrderedDict()
 _RESIDENT_MAX = 32
 
@@ -553,6 +580,7 @@ class ProtoDistributedBatch:
         self.idx_range: Tuple[int, int] = (0, 0)
         self.n_id = None
         self.x = None
+        self.owners: tuple = ()  # distinct allocations the tensors above are views of
 
 
 def _batch_ranges(n: int, cfg: Config) -> List[Tuple[int, int]]:
@@ -597,6 +625,7 @@ class _Slot:
     def __init__(self, sz: SamplerSizes, device, max_bs: int, split_words: int):
         self.ws = _Workspace(sz, device)
         self.stream = torch.cuda.Stream(device)
+        self.stream_raw = (self.stream.stream_id, self.stream.device_index, self.stream.device_type)
         self.event = torch.cuda.Event()
         self.meta_host = torch.empty(SPP_META_WORDS + SPP_MAX_PARTS + 2, dtype=torch.int64).pin_memory()
         self.seeds = torch.empty(max(max_bs, 1), dtype=torch.int64, device=device)
@@ -932,7 +961,15 @@ class Session:
             slot.ticket = None
         else:
             j = slot.cjob
-            with torch.cuda.stream(slot.stream):  # the outputs belong to the slot's stream
+            # the outputs belong to the slot's stream
+            if _FAST_STREAMS:
+                prev = _get_stream_raw(self._device.index)
+                _set_stream_raw(stream_id=slot.stream_raw[0], device_index=slot.stream_raw[1],
+                                device_type=slot.stream_raw[2])
+            else:
+                prev = torch.cuda.current_stream(self._device)
+                torch.cuda.set_stream(slot.stream)
+            try:
                 # one allocation for every structure output of the batch (rowptr / col per hop, and
                 # n_id / bucket ids / perm in distributed mode); exact-size views are cut in
                 # _finalize once the meta block has arrived
@@ -941,12 +978,16 @@ class Session:
                 if j.feature_mode:
                     x = torch.empty((ws.max_nodes, fdim), dtype=fdtype, device=self._device)
                 y = None
-                if self._y is not None:
-                    if self._y_in_arena:  # int64 labels live at the tail of the arena
-                        yo = self._arena_y
-                        y = arena[yo:yo + bs * self._y.size(-1)].view(bs, self._y.size(-1))
-                    else:
-                        y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
+                if self._y is not None and not self._y_in_arena:
+                    y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
+            finally:
+                if _FAST_STREAMS:
+                    _set_stream_raw(stream_id=prev[0], device_index=prev[1], device_type=prev[2])
+                else:
+                    torch.cuda.set_stream(prev)
+            if self._y is not None and self._y_in_arena:  # int64 labels live at the tail of the arena
+                yo = self._arena_y
+                y = arena[yo:yo + bs * self._y.size(-1)].view(bs, self._y.size(-1))
             base = arena.data_ptr()
             for h, (ro, co) in enumerate(self._arena_off):
                 j.out_rowptr[h] = base + 8 * ro
@@ -974,7 +1015,6 @@ class Session:
                 j.n_id_out = base + 8 * o
                 j.bucket_ids = base + 8 * (o + m)
                 j.perm = base + 8 * (o + 2 * m)
-                job["n_id"], job["bucket_ids"], job["perm"] = arena[o:o + m], arena[o + m:o + 2 * m], arena[o + 2 * m:o + 3 * m]
             job["arena"], job["y"] = arena, y
             if x is not None:
                 job["x"] = x
@@ -1013,32 +1053,56 @@ class Session:
             if m[META_OVERFLOW]:
                 raise SalientB200Error("sampler buffer bound exceeded on the device (SPP_META_OVERFLOW)")
             arena, e_id = job["arena"], _empty_eid(self._device)
-            adjs = []
-            for h in range(L - 1, -1, -1):  # reversed like fast_sampler.cpp:224
+            # every exact-size view of the structure part of the arena in ONE split call: per hop
+            # [rowptr | slack | col | slack] (the slack pieces are dropped)
+            cuts, pos = [], 0
+            for h in range(L):
                 ro, co = self._arena_off[h]
                 T, E = m[h], m[META_EDGES0 + h]
-                adjs.append((arena[ro:ro + T + 1], arena[co:co + E], e_id, (T, m[h + 1])))
+                end = self._arena_off[h + 1][0] if h + 1 < L else self._arena_nid
+                cuts += [T + 1, co - ro - T - 1, E, end - co - E]
+            if cfg.distributed:  # n_id | bucketed ids (P partitions, cached) | perm, each max_nodes wide
+                counts = m[SPP_META_WORDS:]
+                mx, P, nb_ = slot.ws.max_nodes, self._P, m[L]
+                used = sum(counts[:P + 1])
+                cuts += [nb_, mx - nb_] + counts[:P + 1] + [mx - used, nb_, mx - nb_,
+                                                            self._arena_words - self._arena_nid - 3 * mx]
+            else:
+                cuts.append(self._arena_words - self._arena_nid)
+            v = arena.split_with_sizes(cuts)
+            adjs = [(v[4 * h], v[4 * h + 2], e_id, (m[h], m[h + 1])) for h in range(L - 1, -1, -1)]  # reversed like fast_sampler.cpp:224
             nb = m[L]
         start, stop = job["range"]
         if not cfg.distributed:
             x = job["x"]
-            out = (x[:nb] if x.size(0) > nb else x, job["y"], adjs, (start, stop))
+            out = OwnedSample((x[:nb] if x.size(0) > nb else x, job["y"], adjs, (start, stop)))
+            if "arena" in job:
+                out.owners = (x, job["arena"]) if (self._y_in_arena or job["y"] is None) else (x, job["arena"], job["y"])
         else:
-            counts = slot.meta_host[SPP_META_WORDS:].tolist()
             P = self._P
             b = ProtoDistributedBatch()
-            ids = job["bucket_ids"]
-            pos = 0
-            for p in range(P):
-                b.partition_nids.append(ids[pos:pos + counts[p]])
-                pos += counts[p]
-            b.cached_nids = ids[pos:pos + counts[P]]
-            b.perm_partition_to_mfg = job["perm"][:nb]
+            if "ready" in job:
+                counts = slot.meta_host[SPP_META_WORDS:].tolist()
+                ids = job["bucket_ids"]
+                pos = 0
+                for p in range(P):
+                    b.partition_nids.append(ids[pos:pos + counts[p]])
+                    pos += counts[p]
+                b.cached_nids = ids[pos:pos + counts[P]]
+                b.perm_partition_to_mfg = job["perm"][:nb]
+                b.n_id = job["n_id"][:nb]
+            else:
+                q = 4 * L  # first distributed piece of the split above
+                b.n_id = v[q]
+                b.partition_nids = list(v[q + 2:q + 2 + P])
+                b.cached_nids = v[q + 2 + P]
+                b.perm_partition_to_mfg = v[q + 4 + P]
+                b.owners = (job["arena"],) + ((job["x"],) if "x" in job else ()) + \
+                    (() if (self._y_in_arena or job["y"] is None) else (job["y"],))
             b.adjs = adjs
             b.idx_range = (start, stop)
             b.sliced_cpu_labels = job["y"]
-            b.n_id = job["n_id"][:nb]
-            b.x = job["x"][:nb] if "x" in job else None
+            b.x = (job["x"][:nb] if job["x"].size(0) > nb else job["x"]) if "x" in job else None
             fdim, fdtype = self._feat_shape
             if self._x_cpu_dev is not None:
                 # compatibility with gpu_percent < 1 (fast_sampler.cpp:1041-1052,1142-1155): rows of

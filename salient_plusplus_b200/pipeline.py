@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import SPP_META_WORDS, SPP_MAX_PARTS, FeatureMap, check
+from ._lib import SPP_META_WORDS, SPP_MAX_PARTS, BatchJob, FeatureMap, check
 from .fast_sampler import _DeviceGraph, _Workspace, _sampler_sizes
 
 c_vp = ctypes.c_void_p
@@ -68,8 +68,40 @@ class MiniBatchPipeline:
                 s.perm = torch.empty(s.ws.max_nodes, dtype=torch.int64, device=self.device)
                 s.counts = torch.zeros(SPP_MAX_PARTS + 2, dtype=torch.int64, device=self.device)
             s.meta_host = torch.empty(SPP_META_WORDS, dtype=torch.int64).pin_memory()
+            s.job = self._make_job(s)
             self.slots.append(s)
         self.gather_events = None
+
+    def _make_job(self, s: _PipeSlot) -> BatchJob:
+        """The slot's spp_batch_job: the very descriptor a Session submits, with static outputs."""
+        j = BatchJob()
+        ctypes.memset(ctypes.byref(j), 0, ctypes.sizeof(j))
+        j.graph, j.ws = self.g.c, s.ws.c
+        j.n_hops, j.replace = self.L, 0
+        for h in range(self.L):
+            j.sizes[h] = self.sizes[h]
+            j.out_col_cap[h] = int(self.sz.hop_edges[h])
+            j.out_rowptr[h] = s.rowptrs[h].data_ptr()
+            j.out_col[h] = s.cols[h].data_ptr()
+        j.row_bytes = self.row_bytes
+        j.stream = s.stream.cuda_stream
+        if s.x is not None:
+            j.x_out = s.x.data_ptr()
+            if self.fm is not None:
+                j.feature_mode, j.fmap = 2, self.fm
+            else:
+                j.feature_mode, j.table, j.table_pitch = 1, self.x_table.ptr, self.x_table.pitch
+        if self.y_table is not None:
+            j.y_table = self.y_table.data_ptr()
+            j.y_row_bytes = self.y_table.size(-1) * self.y_table.element_size()
+            j.y_out = s.y.data_ptr()
+        if self.split:
+            j.do_split, j.use_cache = 1, int(self.use_cache)
+            if j.feature_mode != 2:
+                j.fmap = self.fm
+            j.bucket_ids, j.perm = s.bucket_ids.data_ptr(), s.perm.data_ptr()
+            j.bucket_counts, j.split_scratch = s.counts.data_ptr(), s.scratch.data_ptr()
+        return j
 
     # -- individual stages (all asynchronous on the slot's stream) ------------------------------
     def sample(self, s: _PipeSlot, seeds_ptr: int, bs: int, rng_seed: int):
@@ -105,15 +137,17 @@ class MiniBatchPipeline:
         """One mini-batch on slot ``slot``; returns the (start, end) events around the feature
         gather when ``time_gather``."""
         s = self.slots[slot]
+        if not time_gather:  # one C call, exactly what the Session's executor issues
+            j = s.job
+            j.seeds_dev, j.batch_size, j.rng_seed = seeds_ptr, bs, rng_seed
+            check(self.lib.spp_batch_enqueue(ctypes.byref(j)), "spp_batch_enqueue")
+            return None
         self.sample(s, seeds_ptr, bs, rng_seed)
         self.owner_split(s)
-        ev = None
-        if time_gather:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            ev[0].record(s.stream)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record(s.stream)
         self.gather(s)
-        if time_gather:
-            ev[1].record(s.stream)
+        ev[1].record(s.stream)
         self.labels(s, seeds_ptr, bs)
         return ev
 

@@ -27,6 +27,8 @@ class ProtoDistributedBatch(NamedTuple):
     # extensions: MFG node list and features already gathered in MFG order by the fused kernel
     n_id: Optional[torch.Tensor] = None
     x: Optional[torch.Tensor] = None
+    # the distinct allocations every tensor above is a view of (record_stream on those is enough)
+    owners: tuple = ()
 
     @classmethod
     def from_fast_sampler(cls, batch):
@@ -36,9 +38,14 @@ class ProtoDistributedBatch(NamedTuple):
                    sliced_cpu_labels=batch.sliced_cpu_labels, cached_nids=batch.cached_nids,
                    perm_partition_to_mfg=batch.perm_partition_to_mfg,
                    adjs=[Adj__from_fast_sampler(adj) for adj in batch.adjs], idx_range=slice(start, stop),
-                   n_id=getattr(batch, "n_id", None), x=getattr(batch, "x", None))
+                   n_id=getattr(batch, "n_id", None), x=getattr(batch, "x", None),
+                   owners=getattr(batch, "owners", ()))
 
     def record_stream(self, stream):
+        if self.owners:
+            for t in self.owners:
+                t.record_stream(stream)
+            return
         for part in self.partition_nids:
             if part.is_cuda:
                 part.record_stream(stream)
@@ -88,6 +95,10 @@ class PreparedBatch(NamedTuple):
     y: Optional[torch.Tensor]
     adjs: List[Adj]
     idx_range: slice
+    # Not a field (the reference unpacks four, driver/models.py:464): the distinct allocations
+    # x / y / adjs are views of.  A Session cuts every structure tensor of a batch out of one arena,
+    # so record_stream on the owners covers all of them (set on OwnedPreparedBatch instances).
+    owners = ()
 
     @classmethod
     def from_proto_batch(cls, x: torch.Tensor, y: Optional[torch.Tensor], proto_batch: ProtoBatch):
@@ -100,10 +111,20 @@ class PreparedBatch(NamedTuple):
     @classmethod
     def from_fast_sampler(cls, prepared_sample):
         x, y, adjs, (start, stop) = prepared_sample
+        owners = getattr(prepared_sample, "owners", None)
+        if owners and cls is PreparedBatch:
+            b = OwnedPreparedBatch(x, y.squeeze() if y is not None else None,
+                                   [Adj__from_fast_sampler(adj) for adj in adjs], slice(start, stop))
+            b.owners = owners
+            return b
         return cls(x=x, y=y.squeeze() if y is not None else None,
                    adjs=[Adj__from_fast_sampler(adj) for adj in adjs], idx_range=slice(start, stop))
 
     def record_stream(self, stream):
+        if self.owners:
+            for t in self.owners:
+                t.record_stream(stream)
+            return
         if self.x is not None and self.x.is_cuda:
             self.x.record_stream(stream)
         if self.y is not None and self.y.is_cuda:
@@ -129,6 +150,10 @@ class PreparedBatch(NamedTuple):
     @property
     def batch_size(self):
         return self.idx_range.stop - self.idx_range.start
+
+
+class OwnedPreparedBatch(PreparedBatch):
+    """A PreparedBatch (same four fields) that also carries ``owners`` as an instance attribute."""
 
 
 @dataclass

@@ -17,7 +17,13 @@ import torch
 
 from . import _lib, fast_sampler
 from ._lib import check
-from .samplers import PreparedBatch, ProtoBatch, ProtoDistributedBatch
+from .samplers import OwnedPreparedBatch, PreparedBatch, ProtoBatch, ProtoDistributedBatch
+
+
+def _current_stream(device) -> torch.cuda.Stream:
+    d = device if isinstance(device, torch.device) else torch.device(device)
+    idx = d.index if d.index is not None else torch.cuda.current_device()
+    return fast_sampler.current_stream_cached(idx)
 
 
 class DeviceIterator(Iterator[List[PreparedBatch]]):
@@ -56,7 +62,7 @@ class DevicePrefetcher(DeviceIterator):
         if not ret:
             raise StopIteration
         for device, batch in zip(self.devices, ret):
-            batch.record_stream(torch.cuda.current_stream(device))
+            batch.record_stream(_current_stream(device))
         self.preload()
         return ret
 
@@ -119,6 +125,10 @@ class DeviceDistributedPrefetcher(DeviceIterator):
                 "all_to_all comparison path")
         self.NUMBER_OF_SENT_BYTES += _feature_bytes(batch, self.rank, batch.x.size(1) * batch.x.element_size())
         y = batch.sliced_cpu_labels
+        if batch.owners:
+            b = OwnedPreparedBatch(batch.x, y.squeeze() if y is not None else None, batch.adjs, batch.idx_range)
+            b.owners = batch.owners
+            return b
         return PreparedBatch(batch.x, y.squeeze() if y is not None else None, batch.adjs, batch.idx_range)
 
     def preload(self, timing=True):
@@ -129,7 +139,7 @@ class DeviceDistributedPrefetcher(DeviceIterator):
         ret = self.next
         if not ret:
             raise StopIteration
-        ret[0].record_stream(torch.cuda.current_stream(self.device))
+        ret[0].record_stream(_current_stream(self.device))
         self.preload()
         return ret
 
@@ -200,6 +210,6 @@ class NcclAllToAllPrefetcher(DeviceIterator):
         ret = self.next
         if not ret:
             raise StopIteration
-        ret[0].record_stream(torch.cuda.current_stream(self.device))
+        ret[0].record_stream(_current_stream(self.device))
         self.preload()
         return ret
