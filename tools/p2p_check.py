@@ -1,7 +1,9 @@
-"""Multi-GPU check of the P2P path (run under torchrun, one rank per GPU):
-  1. correctness: distributed Session with IPC-mapped peer partitions, x == X_global[n_id], the
-     ProtoDistributedBatch fields against the oracle, and the NCCL all_to_all comparison path
-     producing the same x;
+"""Multi-GPU measurements of the P2P path (run under torchrun, one rank per GPU; the parity check
+against the oracle lives in tests/multigpu_check.py):
+  1. comparison: the same distributed mini-batches through the fused P2P gather
+     (DeviceDistributedPrefetcher) and through the reference's protocol of three NCCL all_to_alls
+     per batch (NcclAllToAllPrefetcher, fast_trainer/transferers.py:507-766); identical x required,
+     batches/s of both reported;
   2. bandwidth: spp_gather_partitioned on all-remote rows (pure NVLink inbound) and on all-local
      rows (pure HBM), GB/s per GPU.
 """
@@ -9,13 +11,12 @@ import ctypes
 import json
 import os
 import sys
+import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 import torch.distributed as dist
 
-from oracle import oracle as O
 from salient_plusplus_b200 import _lib, fast_sampler as fs, peer, synthetic as S
 from salient_plusplus_b200.samplers import FastSampler, FastSamplerConfig
 from salient_plusplus_b200.transferers import DeviceDistributedPrefetcher, NcclAllToAllPrefetcher
@@ -27,50 +28,62 @@ dist.init_process_group("nccl", device_id=dev)
 L = _lib.load()
 P = world
 
-# ---- 1. correctness ------------------------------------------------------------------------------
-N, E, F = 200000, 4000000, 128
+# ---- 1. fused P2P gather vs the NCCL all_to_all protocol ----------------------------------------
+N, E, F = 2_000_000, 50_000_000, 128
+B = 48
 rowptr, col = S.powerlaw_graph(N, E, seed=1, device=dev)
 X = S.features(N, F, torch.float16, seed=2, device=dev)
 y = S.labels(N, seed=3, device=dev)
 off = S.equal_partition_offsets(N, P)
 lo, hi = int(off[rank]), int(off[rank + 1])
 x_local = X[lo:hi].clone()
-cv = S.degree_cache_vertices(rowptr, off.to(dev), rank, 5000)
-cache = fs.Cache(rank, P, cv, X[cv].contiguous())
-idx = S.seeds(N, 1024 * 6, seed=11 + rank, lo=lo, hi=hi)
+del X
+from salient_plusplus_b200 import vip as V  # noqa: E402
+# 15 % replicated cache, degree ranked; the rows are pulled out of the owners' partitions over P2P
+cache = V.create_vip_cache(rowptr, col, None, 1024, [15, 10, 5], off, rank, 15.0, x_local,
+                           vip=(rowptr[1:] - rowptr[:-1]).to(torch.float64))
+idx = S.seeds(N, 1024 * B, seed=11 + rank, lo=lo, hi=hi)
 
 
-def make_cfg(use_cache):
+def make_cfg():
     return FastSamplerConfig(x_cpu=torch.empty((0, F), dtype=torch.float16), x_gpu=x_local, y=y, rowptr=rowptr, col=col,
                              idx=idx, batch_size=1024, sizes=[15, 10, 5], skip_nonfull_batch=False, pin_memory=True,
-                             distributed=True, partition_book=fs.RangePartitionBook(rank, P, off),
-                             cache=cache if use_cache else fs.Cache(), force_exact_num_batches=True,
-                             exact_num_batches=6, use_cache=use_cache)
+                             distributed=True, partition_book=fs.RangePartitionBook(rank, P, off), cache=cache,
+                             force_exact_num_batches=True, exact_num_batches=B, use_cache=True)
 
 
-ok = True
-rp_h, col_h = rowptr.cpu().numpy(), col.cpu().numpy()
-for use_cache in (False, True):
-    xs = []
-    it = iter(FastSampler(4, 4, make_cfg(use_cache)))
-    oc = O.Cache(cv.cpu().numpy(), N) if use_cache else None
-    for k, (batch,) in enumerate(DeviceDistributedPrefetcher([dev], it)):
-        st, en = batch.idx_range.start, batch.idx_range.stop
-        on, oa = O.multilayer_sample(idx[st:en].numpy(), [15, 10, 5], rp_h, col_h, rng_mode=O.RNG_COUNTER,
-                                     rng_seed=O.session_rng_seed(en))
-        good = torch.equal(batch.x, X[torch.from_numpy(on).to(dev)])
-        good &= torch.equal(batch.y.cpu(), y[idx[st:en].to(dev)].squeeze().cpu())
-        ok &= bool(good)
-        xs.append(batch.x.clone())
-    # NCCL all_to_all comparison path on the same batches
-    it = iter(FastSampler(4, 4, make_cfg(use_cache)))
-    for k, (batch,) in enumerate(NcclAllToAllPrefetcher([dev], it)):
-        ok &= bool(torch.equal(batch.x, xs[k]))
+def drain(cls, keep):
     dist.barrier()
-print(f"[rank {rank}] correctness {'OK' if ok else 'FAILED'}", flush=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out, nodes = [], 0
+    for (batch,) in cls([dev], iter(FastSampler(4, 6, make_cfg()))):
+        nodes += batch.x.size(0)
+        if keep and len(out) < 4:
+            out.append(batch.x.clone())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), nodes, out
+
+
+drain(DeviceDistributedPrefetcher, False)  # warm-up (slot pools, allocator, NCCL communicators)
+drain(NcclAllToAllPrefetcher, False)
+t_p2p, nodes, xs = drain(DeviceDistributedPrefetcher, True)
+t_nccl, nodes2, xs2 = drain(NcclAllToAllPrefetcher, True)
+same = nodes == nodes2 and all(torch.equal(a, b) for a, b in zip(xs, xs2))
+if rank == 0:
+    print(json.dumps({"comparison": "fused P2P gather vs 3x NCCL all_to_all per batch", "world": P, "batches_per_rank": B,
+                      "graph": f"power law {N} nodes {E} edges, {F}-d fp16, 15% degree-ranked cache",
+                      "identical_x": bool(same), "p2p_batches_per_s": round(P * B / t_p2p, 1),
+                      "nccl_all_to_all_batches_per_s": round(P * B / t_nccl, 1),
+                      "speedup": round(t_nccl / t_p2p, 2)}), flush=True)
+del x_local, cache, rowptr, col
+torch.cuda.empty_cache()
+dist.barrier()
 
 # ---- 2. bandwidth -----------------------------------------------------------------------------------
-del X
 rows_per_part = 4_000_000
 for F, dt in ((128, torch.float16), (768, torch.float16)):
     rb = F * 2
