@@ -228,7 +228,8 @@ void spp_debug_set_timeline(void* dev_ptr);
  * kernel / copy issued by the library is then followed by a timing event on its stream.  end()
  * synchronises the device and returns the marks in issue order: label (0 batch begin, 1 seeds
  * H2D, 2 table clear, 3 seeds init, 4 sample, 5 compact, 6 relabel+sort, 7 export n_id, 8 owner
- * split, 9 feature gather, 10 label gather, 11 meta D2H, 12 join), hop, stream handle and
+ * split, 9 feature gather, 10 label gather, 11 meta D2H, 12 join, 13 degree count + scan, 14 large-row
+ * comparison sort, 15 bitmap row sort), hop, stream handle and
  * milliseconds since the first mark (tools/trace_pipeline.py). */
 int spp_trace_begin(int64_t max_marks);
 int64_t spp_trace_end(int32_t* labels_host, int32_t* hops_host, uint64_t* streams_host,

@@ -169,7 +169,8 @@ def check(rc: int, what: str = "") -> None:
 
 
 TRACE_LABELS = ["batch_begin", "seeds_h2d", "table_clear", "seeds_init", "sample", "compact", "relabel_sort",
-                "export_nid", "owner_split", "feature_gather", "label_gather", "meta_d2h", "join"]
+                "export_nid", "owner_split", "feature_gather", "label_gather", "meta_d2h", "join", "degree_count_scan",
+                "sort_large_rows", "sort_rows_bitmap"]
 
 
 def trace_begin(max_marks: int = 4096) -> None:

@@ -18,7 +18,7 @@ int num_sms();
 // trace is active (spp_trace_begin)
 enum TraceLabel {
   kTrBatchBegin = 0, kTrSeedsH2D, kTrTableClear, kTrSeedsInit, kTrSample, kTrCompact, kTrRelabel,
-  kTrExport, kTrSplit, kTrGather, kTrLabels, kTrMetaD2H, kTrJoin
+  kTrExport, kTrSplit, kTrGather, kTrLabels, kTrMetaD2H, kTrJoin, kTrCount, kTrSortLarge, kTrSortBitmap
 };
 void trace_mark(int label, int hop, cudaStream_t st);
 

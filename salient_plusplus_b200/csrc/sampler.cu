@@ -11,9 +11,15 @@
 // local ids T, T+1, ... in exactly the reference's first-discovery order, and a last pass turns
 // candidate slots into local ids and sorts every row ascending (std::sort, sample_cpu.hpp:126).
 //
-//   General path (full neighbourhood k < 0, with replacement, fan-out > 32), 4-5 kernels per hop:
-//     k_hop_count_scan -> k_hop_sample<mode,G,PPL> -> k_hop_compact -> k_relabel_sort_general
-//     (-> k_sort_large_rows); 64-bit decoupled look-back scans, data-dependent edge counts.
+//   General path (with replacement, fan-out > 32), 4 kernels per hop:
+//     k_hop_count_scan -> k_hop_sample<mode,G,PPL> -> k_hop_compact -> k_relabel_sort_general;
+//     64-bit decoupled look-back scans, data-dependent edge counts.
+//   Full neighbourhood (k < 0: layer-wise inference) shares the count / compact kernels but is
+//     edge parallel where rows can be hubs: k_hop_sample_edges (one thread per candidate, row by
+//     binary search in the scanned out_rowptr) and, for rows longer than 32,
+//     k_sort_rows_bitmap (CTA per row, shared-memory bitmap of the local ids, O(S/32 + n));
+//     k_sort_large_rows (comparison network) only takes rows with repeated neighbours or
+//     batches of more than 1.6 M nodes.
 //   Fused path (1 <= k <= 32, without replacement: every reference configuration), 3 kernels per hop:
 //     k_hop_sample_fused -> k_hop_compact_fused -> k_relabel_sort_fused; see the banner further down.
 //
@@ -29,7 +35,8 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 4;
 constexpr int kScanTile = kScanThreads * kScanItems;  // 1024 items per tile
 constexpr int kSampleThreads = 256;
-constexpr int kMetaWork = 25;       // meta word: number of rows queued for the large-row sorter
+constexpr int kMetaWork = 25;       // meta word: number of rows queued for the CTA-per-row sorters (list: tgt_deg)
+constexpr int kMetaWork2 = 26;      // meta word: rows the bitmap sorter handed on (list: low words of tgt_start)
 constexpr int kWarpSortCap = 1024;  // rows up to this length are sorted by one warp in shared memory
 constexpr int kBlockSortSmemElems = 48 * 1024;  // int32 elements a CTA sorts in shared memory
 
@@ -200,6 +207,7 @@ struct HopParams {
   int32_t hop;
   int32_t fanout;
   int32_t replace;
+  int32_t bitmap_rows;  // != 0: rows longer than 32 go (un-relabelled) to k_sort_rows_bitmap
 };
 
 __global__ void __launch_bounds__(kScanThreads) k_hop_count_scan(const __grid_constant__ HopParams prm) {
@@ -215,6 +223,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_count_scan(const __grid_co
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     prm.out_rowptr[0] = 0;
     prm.meta[kMetaWork] = 0;
+    prm.meta[kMetaWork2] = 0;
     if (T == 0) prm.meta[SPP_META_EDGES(prm.hop)] = 0;
   }
   const int k = prm.fanout;
@@ -271,7 +280,8 @@ __device__ __forceinline__ void emit_candidate(const HopParams& prm, int32_t nod
   prm.out_col[p] = (int64_t)slot;
 }
 
-// kMode 0: every neighbour (fanout < 0); 1: with replacement; 2: without replacement (Floyd)
+// kMode 1: with replacement; 2: without replacement (Floyd).  (Full neighbourhood is edge parallel:
+// k_hop_sample_edges below.)
 template <int kMode, int G, int PPL, bool kCol64>
 __global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_constant__ HopParams prm) {
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
@@ -300,10 +310,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_cons
       deg = prm.tgt_deg[i];
       p0 = prm.out_rowptr[i];
     }
-    if constexpr (kMode == 0) {
-      for (int32_t j = gl; j < deg; j += G)
-        emit_candidate(prm, load_col<kCol64>(prm.col, start + j), Tbase, p0 + j);
-    } else if constexpr (kMode == 1) {
+    if constexpr (kMode == 1) {
       const int32_t c = deg > 0 ? k : 0;
       for (int32_t j = gl; j < c; j += G) {
         const uint32_t pick = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)j), (uint32_t)deg);
@@ -356,6 +363,33 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_cons
         if (valid && j < c) emit_candidate(prm, node[q], Tbase, p0 + j);
       }
     }
+  }
+}
+
+// Full neighbourhood (fanout < 0), edge parallel: one thread per candidate position p.  The owning
+// row is found by a binary search in out_rowptr (the exclusive scan k_hop_count_scan just wrote),
+// so a hub with 10^5 neighbours is spread over 10^5 threads instead of looping in one warp, and
+// consecutive lanes read consecutive col entries.
+template <bool kCol64>
+__global__ void __launch_bounds__(kSampleThreads) k_hop_sample_edges(const __grid_constant__ HopParams prm) {
+  int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
+  if (T > prm.max_targets) T = prm.max_targets;
+  const int64_t E = prm.meta[SPP_META_EDGES(prm.hop)];
+  if (E > prm.max_edges || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_OVERFLOW] = 1;
+    return;
+  }
+  const uint32_t Tbase = (uint32_t)T;
+  const int64_t stride = (int64_t)gridDim.x * kSampleThreads;
+  for (int64_t p = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x; p < E; p += stride) {
+    int64_t lo = 0, hi = T;  // out_rowptr[lo] <= p < out_rowptr[hi]
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(prm.out_rowptr + mid) <= p) lo = mid;
+      else hi = mid;
+    }
+    const int64_t j = p - __ldg(prm.out_rowptr + lo);
+    emit_candidate(prm, load_col<kCol64>(prm.col, prm.tgt_start[lo] + j), Tbase, p);
   }
 }
 
@@ -516,6 +550,11 @@ __global__ void __launch_bounds__(kGeneralWarps * 32) k_relabel_sort_general(con
       }
       v = group_bitonic_sort<32>(v, lane);
       if (lane < n) prm.out_col[p0 + lane] = (int64_t)v;
+    } else if (prm.bitmap_rows) {  // k_sort_rows_bitmap relabels and sorts the row with a whole CTA
+      if (lane == 0) {
+        const unsigned long long w = atomicAdd((unsigned long long*)(prm.meta + kMetaWork), 1ull);
+        prm.tgt_deg[w] = (int32_t)i;
+      }
     } else if (n <= kWarpSortCap) {
       for (int64_t j = lane; j < n; j += 32) {
         const uint32_t slot = (uint32_t)prm.out_col[p0 + j];
@@ -538,12 +577,84 @@ __global__ void __launch_bounds__(kGeneralWarps * 32) k_relabel_sort_general(con
   }
 }
 
-// one CTA per queued long row
-__global__ void __launch_bounds__(256) k_sort_large_rows(const __grid_constant__ HopParams prm) {
-  extern __shared__ int32_t s_big[];
+// Rows of a full-neighbourhood hop longer than 32 entries, one CTA per row: the row's local ids
+// are a (nearly always duplicate-free) subset of [0, S), so they are sorted by setting their bits
+// in a shared-memory bitmap and enumerating the set bits in order -- O(S/32 + n) per row instead
+// of the O(n log^2 n) of a comparison network, which matters for hub rows of 10^4..10^5 entries.
+// `cap_bits` = bitmap capacity of this launch (two launches: a small bitmap with many CTAs per SM
+// and a large one); the launch whose range [min_bits, cap_bits) contains S does the work.  A row
+// with a repeated neighbour (multigraph) is relabelled in place and handed on to
+// k_sort_large_rows through the second work list, like every row when S exceeds both bitmaps.
+__global__ void __launch_bounds__(256) k_sort_rows_bitmap(const __grid_constant__ HopParams prm, const int64_t min_bits,
+                                                          const int64_t cap_bits, const int last) {
+  extern __shared__ uint32_t s_bits[];
+  __shared__ uint32_t s_wsum[8];
+  if (prm.meta[SPP_META_OVERFLOW]) return;
+  const int64_t S = prm.meta[SPP_META_NODES(prm.hop + 1)];
+  const bool mine = S > min_bits && S <= cap_bits;
+  if (!mine && !(last && S > cap_bits)) return;
   const int64_t work = prm.meta[kMetaWork];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* list2 = reinterpret_cast<int32_t*>(prm.tgt_start);  // dead after the sampling kernel
+  const int words = (int)((S + 31) >> 5);
+  const int per = (words + 255) / 256;  // bitmap words per thread in the enumeration
   for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
     const int64_t i = prm.tgt_deg[w];
+    const int64_t p0 = prm.out_rowptr[i];
+    const int64_t n = prm.out_rowptr[i + 1] - p0;
+    int64_t* row = prm.out_col + p0;
+    bool dup = !mine;
+    if (mine)
+      for (int t = tid; t < words; t += 256) s_bits[t] = 0u;
+    __syncthreads();
+    for (int64_t j = tid; j < n; j += 256) {
+      const uint32_t slot = (uint32_t)row[j];
+      const uint32_t l = ~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
+      row[j] = (int64_t)l;  // relabelled in place (what the comparison sorter expects)
+      if (mine) {
+        const uint32_t bit = 1u << (l & 31);
+        if (atomicOr(&s_bits[l >> 5], bit) & bit) dup = true;
+      }
+    }
+    if (__syncthreads_or(dup)) {
+      if (tid == 0) {
+        const unsigned long long q = atomicAdd((unsigned long long*)(prm.meta + kMetaWork2), 1ull);
+        list2[q] = (int32_t)i;
+      }
+      continue;
+    }
+    // enumerate the set bits in order: thread t owns words [t * per, (t + 1) * per)
+    const int w0 = tid * per, w1 = (w0 + per < words) ? w0 + per : words;
+    uint32_t cnt = 0;
+    for (int t = w0; t < w1; ++t) cnt += __popc(s_bits[t]);
+    uint32_t inc = warp_incl_scan(cnt, lane);
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < warp) base += s_wsum[q];
+    uint32_t o = base + inc - cnt;
+    for (int t = w0; t < w1; ++t) {
+      uint32_t m = s_bits[t];
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        row[o++] = (int64_t)(((uint32_t)t << 5) + (uint32_t)b);
+      }
+    }
+    __syncthreads();  // s_bits / s_wsum are reused by the next row
+  }
+}
+
+// one CTA per queued long row (comparison network).  second_list: rows handed on by
+// k_sort_rows_bitmap (already relabelled), otherwise the rows queued by k_relabel_sort_general
+__global__ void __launch_bounds__(256) k_sort_large_rows(const __grid_constant__ HopParams prm, const int second_list) {
+  extern __shared__ int32_t s_big[];
+  const int64_t work = prm.meta[second_list ? kMetaWork2 : kMetaWork];
+  const int32_t* list = second_list ? reinterpret_cast<const int32_t*>(prm.tgt_start) : prm.tgt_deg;
+  for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
+    const int64_t i = list[w];
     const int64_t p0 = prm.out_rowptr[i];
     const int64_t n = prm.out_rowptr[i + 1] - p0;
     int64_t* row = prm.out_col + p0;
@@ -992,6 +1103,7 @@ static int launch_count(const spp_graph* g, int hop, int32_t fanout, int replace
   p.tile_state += kGeneralTileOffset;
   k_hop_count_scan<<<scan_grid(p.max_targets), kScanThreads, 0, st>>>(p);
   SPP_KERNEL_CHECK("k_hop_count_scan");
+  trace_mark(kTrCount, hop, st);
   return 0;
 }
 
@@ -1020,8 +1132,17 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
     int64_t cap = (int64_t)sms * 8;
     return (int)(ctas < cap ? ctas : cap);
   };
+  // full neighbourhood: rows longer than 32 are sorted by the bitmap kernels when the node bound
+  // fits the large bitmap (the device picks the launch by the actual node count)
+  constexpr int64_t kBitsSmall = 128 * 1024, kBitsLarge = 200 * 1024 * 8;
+  const bool bitmap = fanout < 0;
+  p.bitmap_rows = bitmap ? 1 : 0;
   if (fanout < 0) {
-    launch_sample_kernel<0, 32, 1>(p, c64, grid_for(32), st);
+    int64_t ctas = ceil_div(max_edges > 0 ? max_edges : 1, kSampleThreads);
+    const int64_t cap = (int64_t)sms * 8;
+    const int egrid = (int)(ctas < cap ? ctas : cap);
+    if (c64) k_hop_sample_edges<true><<<egrid, kSampleThreads, 0, st>>>(p);
+    else k_hop_sample_edges<false><<<egrid, kSampleThreads, 0, st>>>(p);
   } else if (replace) {
     if (fanout <= 8) launch_sample_kernel<1, 8, 1>(p, c64, grid_for(8), st);
     else if (fanout <= 16) launch_sample_kernel<1, 16, 1>(p, c64, grid_for(16), st);
@@ -1035,10 +1156,12 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
     else launch_sample_kernel<2, 32, 4>(p, c64, grid_for(32), st);
   }
   SPP_KERNEL_CHECK("k_hop_sample");
+  trace_mark(kTrSample, hop, st);
 
   if (int r = reset_tiles(ws, max_edges, st)) return r;
   k_hop_compact<<<scan_grid(max_edges), kScanThreads, 0, st>>>(p);
   SPP_KERNEL_CHECK("k_hop_compact");
+  trace_mark(kTrCompact, hop, st);
 
   const bool small_rows = fanout >= 0 && fanout <= 32;
   if (small_rows) {
@@ -1051,20 +1174,35 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
       default: k_relabel_sort_small<32><<<grid, kSampleThreads, 0, st>>>(p); break;
     }
     SPP_KERNEL_CHECK("k_relabel_sort_small");
+    trace_mark(kTrRelabel, hop, st);
   } else {
     int64_t ctas = ceil_div(p.max_targets > 0 ? p.max_targets : 1, kGeneralWarps);
     int64_t cap = (int64_t)sms * 8;
     k_relabel_sort_general<<<(int)(ctas < cap ? ctas : cap), kGeneralWarps * 32, 0, st>>>(p);
     SPP_KERNEL_CHECK("k_relabel_sort_general");
+    trace_mark(kTrRelabel, hop, st);
     if (fanout < 0 || fanout > kWarpSortCap) {
       static bool attr_set = false;
       const size_t smem = (size_t)kBlockSortSmemElems * sizeof(int32_t);
       if (!attr_set) {
         SPP_CUDA(cudaFuncSetAttribute(k_sort_large_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPP_CUDA(cudaFuncSetAttribute(k_sort_rows_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kBitsLarge / 8)));
         attr_set = true;
       }
-      k_sort_large_rows<<<sms, 256, smem, st>>>(p);
+      if (bitmap) {
+        // small bitmap (16 KB: many CTAs per SM) for the usual batch, large one (200 KB) behind it;
+        // whichever launch does not match the node count returns at once
+        const int64_t rows_cap = p.max_targets < (int64_t)sms * 8 ? p.max_targets : (int64_t)sms * 8;
+        k_sort_rows_bitmap<<<(int)(rows_cap > 0 ? rows_cap : 1), 256, kBitsSmall / 8, st>>>(p, -1, kBitsSmall, 0);
+        SPP_KERNEL_CHECK("k_sort_rows_bitmap");
+        k_sort_rows_bitmap<<<sms, 256, kBitsLarge / 8, st>>>(p, kBitsSmall, kBitsLarge, 1);
+        SPP_KERNEL_CHECK("k_sort_rows_bitmap");
+        trace_mark(kTrSortBitmap, hop, st);
+      }
+      k_sort_large_rows<<<sms, 256, smem, st>>>(p, bitmap ? 1 : 0);
       SPP_KERNEL_CHECK("k_sort_large_rows");
+      trace_mark(kTrSortLarge, hop, st);
     }
   }
   return 0;

@@ -181,6 +181,13 @@ class _DeviceGraph:
         else:
             self.max_degree = 0
         self.c = Graph(self.rowptr.data_ptr(), self.col.data_ptr(), 0, 0, self.num_nodes)
+        self._deg = None
+
+    def degrees(self) -> torch.Tensor:
+        """int64 out-degrees (built on first use: only full-neighbourhood Sessions need them)."""
+        if self._deg is None:
+            self._deg = self.rowptr[1:] - self.rowptr[:-1]
+        return self._deg
 
     @classmethod
     def get(cls, rowptr: torch.Tensor, col: torch.Tensor) -> "_DeviceGraph":
@@ -700,6 +707,18 @@ class Session:
         self.total_blocked_dur = datetime.timedelta(0)
         self.total_blocked_occasions = 0
         self._full = any(s < 0 for s in self._sizes)
+        # Layer-wise inference (driver/models.py:455-480) samples ONE full-neighbourhood hop per
+        # batch: its edge count is the degree sum of the seeds, known before anything is launched,
+        # so those batches take the asynchronous, pipelined path like sampled ones.  Other
+        # full-neighbourhood configurations need the device's counts between hops (stepwise path).
+        self._edge_bound = None
+        self._batch_edges = None
+        if self._full and len(self._sizes) == 1 and self._ranges and os.environ.get("SPP_ASYNC_FULL", "1") != "0":
+            self._batch_edges = self._leading_hop_edges(idx)
+            # the workspace bound is rounded up so Sessions over different seed sets (one per layer
+            # and epoch) find their slots in the pool again; outputs are sized per batch
+            self._edge_bound = -(-max(max(self._batch_edges), 1) // 65536) * 65536
+            self._full = False
         self._y = _resident(cfg.y, None, "y") if cfg.y is not None else None
         if self._y is not None and self._y.dim() == 1:
             self._y = self._y.view(-1, 1)
@@ -708,7 +727,17 @@ class Session:
         if _t: _t.append(time.perf_counter())
         self._row_bytes = self._feat_shape[0] * torch.empty(0, dtype=self._feat_shape[1]).element_size()
         max_bs = max((e - s for s, e in self._ranges), default=0)
-        self._sz = _sampler_sizes(max_bs, self._sizes, self._g)
+        if self._edge_bound is not None:
+            # spp_sampler_sizes bounds a full-neighbourhood hop by targets * max_degree: hand it the
+            # smallest per-target figure that covers the largest batch's exact edge count
+            per_target = -(-self._edge_bound // max(max_bs, 1))
+            sz = SamplerSizes()
+            arr = (ctypes.c_int32 * 1)(self._sizes[0])
+            check(self._lib.spp_sampler_sizes(int(max_bs), arr, 1, 0, self._g.num_nodes, int(per_target),
+                                              ctypes.byref(sz)), "spp_sampler_sizes")
+            self._sz = sz
+        else:
+            self._sz = _sampler_sizes(max_bs, self._sizes, self._g)
         depth = int(os.environ.get("SPP_SESSION_DEPTH", "6"))
         depth = max(1, min(depth, int(max_items_in_queue), max(self._num_total, 1)))
         split_words = int(self._lib.spp_split_scratch_words(self._sz.max_nodes)) if cfg.distributed else 0
@@ -719,21 +748,9 @@ class Session:
         self._slots = [pool.pop() if pool else _Slot(sz, self._device, max_bs, split_words) for _ in range(depth)]
         self._released = False
         # arena layout (int64 words) of one batch's structure outputs, at their upper bounds
-        L = len(self._sizes)
-        self._arena_off = []
-        o = 0
-        for h in range(L):
-            T, E = int(sz.hop_targets[h]), max(int(sz.hop_edges[h]), 1)
-            self._arena_off.append((o, o + T + 1))
-            o += T + 1 + E
-        self._arena_nid = o
-        if cfg.distributed:
-            o += 3 * int(sz.max_nodes)  # n_id, bucket_ids, perm
         self._y_in_arena = self._y is not None and self._y.dtype == torch.int64
-        self._arena_y = o
-        if self._y_in_arena:
-            o += max_bs * self._y.size(-1)
-        self._arena_words = max(o, 1)
+        self._max_bs = max_bs
+        self._lay = self._layout(None)
         self._executor = None
         if not self._full and os.environ.get("SPP_EXECUTOR", "1") != "0":
             self._executor = _executor(self._device.index)
@@ -761,6 +778,18 @@ class Session:
                 (b - a) * 1e6 for a, b in zip(_t[:-1], _t[1:])), flush=True)
 
     # -- set-up -------------------------------------------------------------------------------
+    def _leading_hop_edges(self, idx: torch.Tensor) -> List[int]:
+        """Per-batch edge count of a full-neighbourhood first hop: every seed position is a
+        target (duplicates included, sample_cpu.hpp:36-64), so a batch's count is the degree sum of
+        its slice of idx.  One device pass + one read-back at Session set-up."""
+        g = self._g
+        deg = g.degrees()
+        c = torch.cumsum(deg[idx.to(self._device)], 0)
+        c = torch.cat([c.new_zeros(1), c])
+        st = torch.tensor([a for a, _ in self._ranges], dtype=torch.int64, device=self._device)
+        en = torch.tensor([b for _, b in self._ranges], dtype=torch.int64, device=self._device)
+        return (c[en] - c[st]).tolist()
+
     def _setup_features(self):
         cfg = self._config
         self._fm = None
@@ -848,6 +877,28 @@ class Session:
                 self._fm = make_feature_map(off, self._rank, tables, ctab.storage if ctab else None,
                                             self._cache_map, ptrs, ltab.pitch, ctab.pitch if ctab else 0)
 
+    def _layout(self, edges0: Optional[int]):
+        """(per-hop (rowptr, col) offsets, n_id offset, y offset, total words, node bound) of one
+        batch's int64 arena.  ``edges0``: exact edge count of a leading full-neighbourhood hop (the
+        arena and x of such a batch are sized by it instead of by the Session-wide bound)."""
+        sz, cfg = self._sz, self._config
+        off, o = [], 0
+        m = int(sz.max_nodes)
+        for h in range(len(self._sizes)):
+            T, E = int(sz.hop_targets[h]), max(int(sz.hop_edges[h]), 1)
+            if h == 0 and edges0 is not None:
+                E = max(int(edges0), 1)
+                m = min(m, T + E)
+            off.append((o, o + T + 1))
+            o += T + 1 + E
+        nid = o
+        if cfg.distributed:
+            o += 3 * m  # n_id, bucket_ids, perm
+        yo = o
+        if self._y_in_arena:
+            o += self._max_bs * self._y.size(-1)
+        return off, nid, yo, max(o, 1), m
+
     # -- enqueue / finalise ---------------------------------------------------------------------
     def _init_job(self, slot: "_Slot"):
         """Static part of the slot's spp_batch_job (graph, workspace, tables, fan-outs)."""
@@ -889,9 +940,11 @@ class Session:
         on the slot's stream.  A cache miss there is a cudaMalloc of a few hundred MB (2-30 ms,
         measured), so the first time a slot sees a given output size its pool is primed with the
         blocks a steady-state pipeline needs (in flight + held by the consumer + prefetched)."""
+        if self._batch_edges is not None:
+            return  # outputs are sized batch by batch
         fdim, fdtype = self._feat_shape
         x_rows = slot.ws.max_nodes if slot.cjob.feature_mode else 0
-        key = (self._arena_words, x_rows, fdim, fdtype)
+        key = (self._lay[3], x_rows, fdim, fdtype)
         primed = getattr(slot, "primed", None)
         if primed is None:
             primed = slot.primed = set()
@@ -901,7 +954,7 @@ class Session:
         with torch.cuda.stream(slot.stream):
             keep = []
             for _ in range(blocks):
-                keep.append(torch.empty(self._arena_words, dtype=torch.int64, device=self._device))
+                keep.append(torch.empty(self._lay[3], dtype=torch.int64, device=self._device))
                 if x_rows:
                     keep.append(torch.empty((x_rows, fdim), dtype=fdtype, device=self._device))
             del keep
@@ -909,6 +962,7 @@ class Session:
     def _enqueue(self):
         slot = self._free.popleft()
         start, stop = self._ranges[self._next]
+        lay = self._lay if self._batch_edges is None else self._layout(self._batch_edges[self._next])
         self._next += 1
         bs = stop - start
         cfg = self._config
@@ -973,10 +1027,10 @@ class Session:
                 # one allocation for every structure output of the batch (rowptr / col per hop, and
                 # n_id / bucket ids / perm in distributed mode); exact-size views are cut in
                 # _finalize once the meta block has arrived
-                arena = torch.empty(self._arena_words, dtype=torch.int64, device=self._device)
+                arena = torch.empty(lay[3], dtype=torch.int64, device=self._device)
                 x = None
                 if j.feature_mode:
-                    x = torch.empty((ws.max_nodes, fdim), dtype=fdtype, device=self._device)
+                    x = torch.empty((lay[4], fdim), dtype=fdtype, device=self._device)
                 y = None
                 if self._y is not None and not self._y_in_arena:
                     y = torch.empty((bs, self._y.size(-1)), dtype=self._y.dtype, device=self._device)
@@ -986,12 +1040,14 @@ class Session:
                 else:
                     torch.cuda.set_stream(prev)
             if self._y is not None and self._y_in_arena:  # int64 labels live at the tail of the arena
-                yo = self._arena_y
+                yo = lay[2]
                 y = arena[yo:yo + bs * self._y.size(-1)].view(bs, self._y.size(-1))
             base = arena.data_ptr()
-            for h, (ro, co) in enumerate(self._arena_off):
+            for h, (ro, co) in enumerate(lay[0]):
                 j.out_rowptr[h] = base + 8 * ro
                 j.out_col[h] = base + 8 * co
+            if self._batch_edges is not None:
+                j.out_col_cap[0] = max(int(self._batch_edges[self._next - 1]), 0)
             if self._idx_host is not None:
                 # the executor thread copies straight out of the caller's idx memory (an 8 KB
                 # cudaMemcpyAsync; pageable sources are staged by the driver); the Session keeps
@@ -1011,11 +1067,11 @@ class Session:
             j.x_out = x.data_ptr() if x is not None else None
             j.y_out = y.data_ptr() if (y is not None and bs) else None
             if cfg.distributed:
-                o, m = self._arena_nid, ws.max_nodes
+                o, m = lay[1], lay[4]
                 j.n_id_out = base + 8 * o
                 j.bucket_ids = base + 8 * (o + m)
                 j.perm = base + 8 * (o + 2 * m)
-            job["arena"], job["y"] = arena, y
+            job["arena"], job["y"], job["lay"] = arena, y, lay
             if x is not None:
                 job["x"] = x
             elif not cfg.distributed:
@@ -1055,20 +1111,20 @@ class Session:
             arena, e_id = job["arena"], _empty_eid(self._device)
             # every exact-size view of the structure part of the arena in ONE split call: per hop
             # [rowptr | slack | col | slack] (the slack pieces are dropped)
-            cuts, pos = [], 0
+            a_off, a_nid, _, a_words, mx = job["lay"]
+            cuts = []
             for h in range(L):
-                ro, co = self._arena_off[h]
+                ro, co = a_off[h]
                 T, E = m[h], m[META_EDGES0 + h]
-                end = self._arena_off[h + 1][0] if h + 1 < L else self._arena_nid
+                end = a_off[h + 1][0] if h + 1 < L else a_nid
                 cuts += [T + 1, co - ro - T - 1, E, end - co - E]
-            if cfg.distributed:  # n_id | bucketed ids (P partitions, cached) | perm, each max_nodes wide
+            if cfg.distributed:  # n_id | bucketed ids (P partitions, cached) | perm, each `mx` wide
                 counts = m[SPP_META_WORDS:]
-                mx, P, nb_ = slot.ws.max_nodes, self._P, m[L]
+                P, nb_ = self._P, m[L]
                 used = sum(counts[:P + 1])
-                cuts += [nb_, mx - nb_] + counts[:P + 1] + [mx - used, nb_, mx - nb_,
-                                                            self._arena_words - self._arena_nid - 3 * mx]
+                cuts += [nb_, mx - nb_] + counts[:P + 1] + [mx - used, nb_, mx - nb_, a_words - a_nid - 3 * mx]
             else:
-                cuts.append(self._arena_words - self._arena_nid)
+                cuts.append(a_words - a_nid)
             v = arena.split_with_sizes(cuts)
             adjs = [(v[4 * h], v[4 * h + 2], e_id, (m[h], m[h + 1])) for h in range(L - 1, -1, -1)]  # reversed like fast_sampler.cpp:224
             nb = m[L]

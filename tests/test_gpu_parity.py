@@ -144,6 +144,51 @@ def test_long_rows_sort_paths(fs):
     assert adjs_equal(adjs, oa)
 
 
+def _rows_graph(rows, n):
+    rowptr, col = [0], []
+    for r in rows:
+        col.append(np.asarray(r, dtype=np.int64))
+        rowptr.append(rowptr[-1] + len(r))
+    rowptr += [rowptr[-1]] * (n - len(rows))
+    return torch.tensor(rowptr, dtype=torch.int64), torch.from_numpy(np.concatenate(col))
+
+
+def test_full_rows_with_repeated_neighbours(fs):
+    """Multigraph rows: a repeated neighbour defeats the bitmap row sort, so those rows must reach
+    the comparison sorter (second work list) while clean rows of the same hop stay on the bitmap."""
+    n = 20000
+    rng = np.random.default_rng(11)
+    rows = [rng.permutation(n)[:300],                                   # clean, > 32
+            np.concatenate([rng.permutation(n)[:200], [7, 7, 7]]),       # one id three times
+            rng.integers(0, 50, size=400),                               # heavy repetition
+            rng.permutation(n)[:3000],                                   # clean, > 1024
+            np.concatenate([rng.permutation(n)[:2000], rng.permutation(n)[:2000]]),  # many pairs
+            rng.permutation(n)[:20]]                                     # register path
+    rowptr, col = _rows_graph(rows, n)
+    idx = torch.arange(len(rows), dtype=torch.int64)
+    n_id, adjs = fs.multilayer_sample(idx, [-1], rowptr, col)
+    on, oa = O.multilayer_sample(idx.numpy(), [-1], rowptr.numpy(), col.numpy())
+    assert np.array_equal(n_id.cpu().numpy(), on)
+    assert adjs_equal(adjs, oa)
+
+
+@pytest.mark.parametrize("n,row_len,n_rows", [(400_000, 30_000, 9), (2_600_000, 45_000, 42)])
+def test_full_rows_large_node_counts(fs, n, row_len, n_rows):
+    """Node counts beyond the small bitmap (128 K ids: second launch with the 200 KB bitmap) and
+    beyond both bitmaps (1.6 M ids: every long row falls back to the comparison sorter)."""
+    rng = np.random.default_rng(13)
+    perm = rng.permutation(n)
+    rows = [perm[i * row_len:(i + 1) * row_len][rng.permutation(row_len)] for i in range(n_rows)]
+    rows.append(perm[:40])
+    rowptr, col = _rows_graph(rows, n)
+    idx = torch.arange(len(rows), dtype=torch.int64)
+    n_id, adjs = fs.multilayer_sample(idx, [-1], rowptr, col)
+    on, oa = O.multilayer_sample(idx.numpy(), [-1], rowptr.numpy(), col.numpy())
+    assert n_id.numel() > (128 * 1024 if n < 1_000_000 else 1_638_400)
+    assert np.array_equal(n_id.cpu().numpy(), on)
+    assert adjs_equal(adjs, oa)
+
+
 def test_empty_and_isolated(fs):
     rowptr, col = bounded_degree_graph(n=50, max_deg=0)
     n_id, adjs = fs.multilayer_sample(torch.tensor([3, 4, 5]), [15, 10], rowptr, col)

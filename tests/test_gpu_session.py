@@ -297,3 +297,59 @@ def test_remote_frequency_statistics(fs, data):
     assert np.array_equal(want[v], f)
     top = sess.get_n_most_freq_remote_vertices(10).numpy()
     assert np.array_equal(top, v[:10]) and want[top].min() >= np.sort(want)[-10]
+
+
+@pytest.mark.parametrize("async_full", ["1", "0"])
+def test_session_single_full_hop_async_and_stepwise(fs, data, monkeypatch, async_full):
+    """Layer-wise inference batches (sizes [-1]): the pipelined path sized by the seeds' degree sum
+    and the stepwise path must both reproduce the oracle, duplicates among the seeds included."""
+    monkeypatch.setenv("SPP_ASYNC_FULL", async_full)
+    rowptr, col, x, y, N = data
+    base = S.seeds(N, 400)
+    idx = torch.cat([base, base[:37], torch.arange(64)])      # duplicates + a run of consecutive ids
+    cfg = _config(fs, x, y, rowptr, col, idx, sizes=[-1], batch_size=96)
+    sess = fs.Session(4, 6, cfg)
+    assert (sess._edge_bound is not None) == (async_full == "1")
+    deg = (rowptr[1:] - rowptr[:-1])
+    n = 0
+    while True:
+        b = sess.blocking_get_batch()
+        if b is None:
+            break
+        xb, yb, adjs, (st, en) = b
+        on, oa = O.multilayer_sample(idx[st:en].numpy(), [-1], rowptr.numpy(), col.numpy())
+        assert adjs_equal(adjs, oa)
+        assert adjs[0][1].numel() == int(deg[idx[st:en]].sum())
+        assert torch.equal(xb.cpu(), x[torch.from_numpy(on)])
+        assert torch.equal(yb.cpu(), y[idx[st:en]])
+        n += 1
+    assert n == sess.num_total_batches == (idx.numel() + 95) // 96
+
+
+def test_session_distributed_single_full_hop(fs, data):
+    rowptr, col, x, y, N = data
+    P, rank = 4, 2
+    off = S.equal_partition_offsets(N, P)
+    lo, hi = int(off[rank]), int(off[rank + 1])
+    idx = torch.arange(lo, hi, dtype=torch.int64)[:300]
+    cfg = _config(fs, torch.empty((0, x.size(1)), dtype=x.dtype), y, rowptr, col, idx, distributed=True, use_cache=False,
+                  sizes=[-1])
+    cfg.x_gpu = x[lo:hi].contiguous()
+    cfg.partition_book = fs.RangePartitionBook(rank, P, off)
+    cfg.cache = fs.Cache()
+    cfg.partition_tables = [x[int(off[p]):int(off[p + 1])].contiguous() if p != rank else None for p in range(P)]
+    sess = fs.Session(2, 8, cfg)
+    assert sess._edge_bound is not None
+    for want in O.batch_ranges(idx.numel(), 64, False, False, 0):
+        b = sess.blocking_get_batch_distributed()
+        assert tuple(b.idx_range) == want
+        st, en = want
+        on, oa = O.multilayer_sample(idx[st:en].numpy(), [-1], rowptr.numpy(), col.numpy())
+        pn, cn, perm, _ = O.distributed_binning(on, off.numpy(), rank, P, hi - lo, False, None)
+        assert adjs_equal(b.adjs, oa)
+        for a, w in zip(b.partition_nids, pn):
+            assert np.array_equal(a.cpu().numpy(), w)
+        assert np.array_equal(b.perm_partition_to_mfg.cpu().numpy(), perm)
+        assert np.array_equal(b.n_id.cpu().numpy(), on)
+        assert torch.equal(b.x.cpu(), x[torch.from_numpy(on)])
+    assert sess.blocking_get_batch_distributed() is None
