@@ -455,6 +455,11 @@ def ours(args):
         tl = tn
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    try:  # time the consumer spent waiting for a batch that was not ready (GPU- or issue-bound share)
+        st_ = e2e_iter.it.get_stats()
+        blocked_us, blocked_n = st_.total_blocked_dur.total_seconds() * 1e6, int(st_.total_blocked_occasions)
+    except Exception:  # noqa: BLE001
+        blocked_us, blocked_n = None, None
     clk = clocks.stop()
     first_us = lat[0] * 1e6
     top3 = sorted(range(len(lat)), key=lambda i: -lat[i])[:3]
@@ -539,7 +544,9 @@ def ours(args):
                     "gathered_GBps": round(world * e2e_nodes * row_bytes / t_e2e / 1e9, 2),
                     "api": "FastSampler -> " + ("DeviceDistributedPrefetcher" if P > 1 else "DevicePrefetcher"),
                     "per_batch_us": {"p50": round(lat[len(lat) // 2] * 1e6, 1), "p90": round(lat[int(len(lat) * 0.9)] * 1e6, 1),
-                                     "max": round(lat[-1] * 1e6, 1), "first": round(first_us, 1), "setup": round(t_setup * 1e6, 1), "slowest_iters": top3}},
+                                     "max": round(lat[-1] * 1e6, 1), "first": round(first_us, 1), "setup": round(t_setup * 1e6, 1), "slowest_iters": top3,
+                                     "consumer_blocked_us_total": None if blocked_us is None else round(blocked_us, 1),
+                                     "consumer_blocked_batches": blocked_n}},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_gather (feature gather)", "achieved": round(achieved, 1),

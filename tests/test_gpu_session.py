@@ -353,3 +353,19 @@ def test_session_distributed_single_full_hop(fs, data):
         assert np.array_equal(b.n_id.cpu().numpy(), on)
         assert torch.equal(b.x.cpu(), x[torch.from_numpy(on)])
     assert sess.blocking_get_batch_distributed() is None
+
+
+def test_side_stream_fork_is_bit_exact():
+    """SPP_FORK=3 (relabel/sort kernels and the feature gather forked onto side streams; read once
+    per process by the library) must not change any result: the Session tests above are re-run in
+    a child process with the switch on."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPP_FORK="3")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_session.py"), "-q", "-x",
+                        "-m", "gpu", "-k", "test_session_nondistributed or test_session_distributed_single_process"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
