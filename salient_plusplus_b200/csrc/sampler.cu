@@ -65,13 +65,9 @@ __device__ __forceinline__ uint32_t table_insert(const Table& t, int32_t key) {
     __stcg(t.w + 2 * (size_t)slot, want);
     return slot;
   }
-  while (true) {
-    uint32_t k = __ldcg(t.w + 2 * (size_t)slot);
-    if (k == want) return slot;
-    if (k == 0u) {
-      uint32_t prev = atomicCAS(t.w + 2 * (size_t)slot, 0u, want);
-      if (prev == 0u || prev == want) return slot;
-    }
+  while (true) {  // optimistic: one L2 round trip when the slot is free or already holds the key
+    const uint32_t prev = atomicCAS(t.w + 2 * (size_t)slot, 0u, want);
+    if (prev == 0u || prev == want) return slot;
     slot = (slot + 1) & t.mask;
   }
 }
@@ -697,20 +693,6 @@ constexpr uint32_t kInvalidCand = 0xFFFFFFFFu;
 constexpr int kFusedItems = 8;
 constexpr int kFusedTile = kScanThreads * kFusedItems;  // 2048 virtual positions per tile
 
-__device__ __forceinline__ uint32_t table_insert_optimistic(const Table& t, int32_t key) {
-  const uint32_t want = (uint32_t)key + 1u;
-  uint32_t slot = table_home(t, key);
-  if (t.direct) {
-    __stcg(t.w + 2 * (size_t)slot, want);
-    return slot;
-  }
-  while (true) {
-    const uint32_t prev = atomicCAS(t.w + 2 * (size_t)slot, 0u, want);
-    if (prev == 0u || prev == want) return slot;
-    slot = (slot + 1) & t.mask;
-  }
-}
-
 struct FusedParams {
   HopParams h;
   uint32_t* cand;    // uint32[T * k] slot of every virtual candidate
@@ -806,7 +788,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __gri
     }
     // ---- stage C: insert the previous round's candidate ------------------------------------------
     if (c_valid) {
-      const uint32_t slot = table_insert_optimistic(prm.tab, c_node);
+      const uint32_t slot = table_insert(prm.tab, c_node);
       atomicMax(prm.tab.w + 2 * (size_t)slot + 1, ~(Tbase + c_v));
       fp.cand[c_v] = slot;
     }
@@ -1194,10 +1176,14 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
         // small bitmap (16 KB: many CTAs per SM) for the usual batch, large one (200 KB) behind it;
         // whichever launch does not match the node count returns at once
         const int64_t rows_cap = p.max_targets < (int64_t)sms * 8 ? p.max_targets : (int64_t)sms * 8;
-        k_sort_rows_bitmap<<<(int)(rows_cap > 0 ? rows_cap : 1), 256, kBitsSmall / 8, st>>>(p, -1, kBitsSmall, 0);
+        const bool small_only = p.max_targets + max_edges <= kBitsSmall;  // host bound on the node count
+        k_sort_rows_bitmap<<<(int)(rows_cap > 0 ? rows_cap : 1), 256, kBitsSmall / 8, st>>>(p, -1, kBitsSmall,
+                                                                                            small_only ? 1 : 0);
         SPP_KERNEL_CHECK("k_sort_rows_bitmap");
-        k_sort_rows_bitmap<<<sms, 256, kBitsLarge / 8, st>>>(p, kBitsSmall, kBitsLarge, 1);
-        SPP_KERNEL_CHECK("k_sort_rows_bitmap");
+        if (!small_only) {
+          k_sort_rows_bitmap<<<sms, 256, kBitsLarge / 8, st>>>(p, kBitsSmall, kBitsLarge, 1);
+          SPP_KERNEL_CHECK("k_sort_rows_bitmap");
+        }
         trace_mark(kTrSortBitmap, hop, st);
       }
       k_sort_large_rows<<<sms, 256, smem, st>>>(p, bitmap ? 1 : 0);
