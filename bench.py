@@ -328,8 +328,11 @@ def ours(args):
         if world > 1:
             dist.barrier()
 
-    pipe = MiniBatchPipeline(rowptr, col32, sizes, bs, x_table=None if fm is not None else x_local, y_table=y,
-                             feature_map=fm, feat_dim=f, feat_dtype=dt, split=False, depth=args.depth, device=dev)
+    if args.no_features and args.device_only:
+        pipe = MiniBatchPipeline(rowptr, col32, sizes, bs, depth=args.depth, device=dev)
+    else:
+        pipe = MiniBatchPipeline(rowptr, col32, sizes, bs, x_table=None if fm is not None else x_local, y_table=y,
+                                 feature_map=fm, feat_dim=f, feat_dtype=dt, split=False, depth=args.depth, device=dev)
     D = len(pipe.slots)
     main = torch.cuda.current_stream()
 
@@ -362,7 +365,9 @@ def ours(args):
     e0.record(main)
     for s in pipe.slots:
         s.stream.wait_event(e0)
+    t_issue0 = time.perf_counter()
     run_batches(W, K)
+    t_issue = time.perf_counter() - t_issue0  # host time spent issuing the K batches
     for s in pipe.slots:
         main.wait_stream(s.stream)
     e1.record(main)
@@ -378,6 +383,7 @@ def ours(args):
         if rank == 0:
             print(json.dumps({"device_only": True, "batches_per_s": round(world * K / (ms * 1e-3), 1),
                               "us_per_batch": round(1000.0 * ms / K, 2), "launches": launches,
+                              "host_issue_us_per_batch": round(1e6 * t_issue / K, 2),
                               "env": {k: v for k, v in os.environ.items() if k.startswith("SPP_")}}), flush=True)
         if world > 1:
             dist.barrier()
@@ -582,6 +588,8 @@ def main():
                     help="probability that an edge stays inside its source's partition block (0 = locality-free "
                          "Chung-Lu graph, the worst case for range-partitioned features)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-features", action="store_true",
+                    help="A/B experiments with --device-only: sampler alone (no feature / label gather)")
     ap.add_argument("--device-only", action="store_true",
                     help="A/B experiments: print the device-timed batches/s and exit (not a bench line)")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile the public-API loop (stderr)")
