@@ -311,6 +311,15 @@ def ours(args):
         # ... and fills its replicated cache by pulling the chosen rows out of the owners'
         # partitions with the P2P gather kernel (replaces the three blocking all_to_alls of
         # ddp.py:524-551)
+        if str(args.cache_pct).lower() == "auto":
+            # B200-first replication factor: as many of the hottest remote rows as fit in a fixed share
+            # (a quarter) of the HBM that is still free, capped at "everything" (alpha = (P-1) * 100 %
+            # of a partition, in the reference's units: ddp.py:421)
+            free_b, _ = torch.cuda.mem_get_info()
+            part_rows = max(1, n // P)
+            args.cache_pct = round(min((P - 1) * 100.0, 100.0 * (free_b // 4) / (part_rows * ltab.pitch)), 2)
+        else:
+            args.cache_pct = float(args.cache_pct)
         cache = V.create_vip_cache(rowptr, col32, None, bs, sizes, off, rank, args.cache_pct, x_local,
                                    partition_tables=part_tensors, peer_table_ptrs=ptrs, vip=probs)
         del probs
@@ -581,7 +590,9 @@ def main():
     ap.add_argument("--workload", default="products", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (testing only)")
     ap.add_argument("--depth", type=int, default=6, help="mini-batches in flight (CUDA streams)")
-    ap.add_argument("--cache-pct", type=float, default=15.0)
+    ap.add_argument("--cache-pct", default="15.0",
+                    help="replicated rows per GPU in %% of a partition (the reference's alpha, default its documented "
+                         "15); 'auto' = whatever fits a quarter of the free HBM, up to every remote row")
     ap.add_argument("--parts", type=int, default=0, help="feature partitions (default: one per GPU)")
     ap.add_argument("--cache-policy", default="vip", choices=["vip", "degree"])
     ap.add_argument("--locality", type=float, default=0.0,

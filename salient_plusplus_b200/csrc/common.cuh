@@ -34,6 +34,9 @@ AuxStreams* aux_streams(cudaStream_t main);
 // (SPP_FORK overrides the default)
 int pipeline_flags();
 
+// true when `p` is a pointer spp_ipc_import returned (a peer GPU's memory mapped into this process)
+bool ipc_imported(const void* p);
+
 // sampler.cu
 int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batch_size, const int32_t* sizes,
                           int n_hops, int replace, uint64_t rng_seed, const spp_sampler_ws* ws,

@@ -177,28 +177,27 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
   }
 }
 
-static int gather_ctas_per_sm() {
-  static int v = 0;
-  if (v == 0) {
+// 0 = not forced by the environment
+static int gather_ctas_per_sm_env() {
+  static int v = -1;
+  if (v < 0) {
     const char* e = getenv("SPP_GATHER_CTAS_PER_SM");
-    v = (e && atoi(e) > 0) ? atoi(e) : 4;
+    v = (e && atoi(e) > 0) ? atoi(e) : 0;
   }
   return v;
 }
 
-// Experiment hook: SPP_L2_FETCH_GRANULARITY=32|64|128 sets cudaLimitMaxL2FetchGranularity once.
-static void maybe_set_fetch_granularity() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  const char* e = getenv("SPP_L2_FETCH_GRANULARITY");
-  if (e && *e) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+// Does any partition table live on another GPU?  Peer tables enter a process through
+// spp_ipc_import, which remembers the pointers it handed out (runtime.cu).
+static bool map_has_peer_tables(const GatherParams& prm) {
+  for (int p = 0; p < prm.book.num_parts; ++p)
+    if (p != prm.book.rank && prm.tables[p] != nullptr && ipc_imported(prm.tables[p])) return true;
+  return false;
 }
 
 template <bool kPartitioned>
 static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaStream_t st) {
   if (prm.n_max <= 0) return 0;
-  maybe_set_fetch_granularity();
   prm.vpr = (uint32_t)(prm.row_bytes / vec_bytes);
   if ((uint64_t)prm.vpr * kRows >= (1ull << 31))
     return fail(SPP_EUNSUPPORTED, "gather: row of %lld bytes too wide", (long long)prm.row_bytes);
@@ -206,8 +205,18 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
   prm.vpr_magic = magic_ok ? (uint32_t)(((1ull << 32) + prm.vpr - 1) / prm.vpr) : 0u;
   const int64_t tiles = ceil_div(prm.n_max, kRows);
   // 4 CTAs / SM x 8 loads in flight per thread saturate HBM and leave half of every SM's thread
-  // slots to the latency-bound sampler kernels of the other in-flight mini-batches
-  const int64_t max_ctas = (int64_t)num_sms() * gather_ctas_per_sm();
+  // slots to the latency-bound sampler kernels of the other in-flight mini-batches.  When rows
+  // come from peer GPUs the kernel is NVLink bound (~630 GB/s needs < 2 MB in flight) and holds
+  // its CTAs 3-5x longer: 2 CTAs / SM keep the link just as busy and leave the sampler kernels of
+  // the other in-flight batches three quarters of every SM (+2.6 % at 2 GPUs, +6.6 % at 4 on the
+  // products shape, profiles/r01_ab_multi_gather_ctas.txt)
+  int cps = gather_ctas_per_sm_env();
+  if (cps == 0) {
+    cps = 4;
+    if constexpr (kPartitioned)
+      if (map_has_peer_tables(prm)) cps = 2;
+  }
+  const int64_t max_ctas = (int64_t)num_sms() * cps;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
 #define SPP_GATHER_LAUNCH(V)                                                                    \
   do {                                                                                          \

@@ -67,6 +67,17 @@ void trace_mark(int label, int hop, cudaStream_t st) {
   g_trace.push_back({label, hop, st, ev});
 }
 
+// ---- pointers handed out by spp_ipc_import (peer GPUs' memory) ------------------------------------
+static std::mutex g_ipc_mu;
+static std::vector<const void*> g_ipc_ptrs;
+
+bool ipc_imported(const void* p) {
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  for (const void* q : g_ipc_ptrs)
+    if (q == p) return true;
+  return false;
+}
+
 // ---- side streams ----------------------------------------------------------------------------
 static std::mutex g_aux_mu;
 static std::vector<std::pair<cudaStream_t, AuxStreams*>> g_aux;
@@ -177,11 +188,23 @@ int spp_ipc_import(const uint8_t* handle_host, int64_t offset, void** ptr_host) 
   void* base = nullptr;
   SPP_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
   *ptr_host = (void*)((uintptr_t)base + (uintptr_t)offset);
+  {
+    std::lock_guard<std::mutex> lk(spp::g_ipc_mu);
+    spp::g_ipc_ptrs.push_back(*ptr_host);
+  }
   return 0;
 }
 
 int spp_ipc_close(void* ptr, int64_t offset) {
   if (!ptr) return 0;
+  {
+    std::lock_guard<std::mutex> lk(spp::g_ipc_mu);
+    for (size_t i = 0; i < spp::g_ipc_ptrs.size(); ++i)
+      if (spp::g_ipc_ptrs[i] == ptr) {
+        spp::g_ipc_ptrs.erase(spp::g_ipc_ptrs.begin() + i);
+        break;
+      }
+  }
   SPP_CUDA(cudaIpcCloseMemHandle((void*)((uintptr_t)ptr - (uintptr_t)offset)));
   return 0;
 }
