@@ -68,3 +68,48 @@ def test_adj_and_batches():
 
 def test_struct_sizes_stable():
     assert ctypes.sizeof(_lib.BatchJob) == 832
+
+
+def test_prepared_batch_keeps_four_fields_and_owner_fast_path():
+    """The reference unpacks a PreparedBatch into four values (driver/models.py:464), so `owners`
+    must stay an attribute; record_stream must touch exactly the owners when they are known."""
+    from salient_plusplus_b200.fast_sampler import OwnedSample
+    from salient_plusplus_b200.samplers import OwnedPreparedBatch
+
+    class Probe:
+        def __init__(self):
+            self.calls = 0
+            self.is_cuda = True
+
+        def record_stream(self, stream):
+            self.calls += 1
+
+    rowptr, col = torch.tensor([0, 1, 3]), torch.tensor([2, 0, 1])
+    sample = OwnedSample((torch.zeros(3, 4), torch.zeros(2, 1), [(rowptr, col, torch.empty(0), (2, 3))], (5, 7)))
+    a, b = Probe(), Probe()
+    sample.owners = (a, b)
+    pb = PreparedBatch.from_fast_sampler(sample)
+    assert isinstance(pb, OwnedPreparedBatch) and isinstance(pb, PreparedBatch) and len(pb) == 4
+    x, y, adjs, rng = pb                                     # four-way unpacking still works
+    assert rng == slice(5, 7) and PreparedBatch._fields == ("x", "y", "adjs", "idx_range")
+    pb.record_stream(object())
+    assert (a.calls, b.calls) == (1, 1)
+    plain = PreparedBatch.from_fast_sampler(tuple(sample))   # no owners: per-tensor path, CPU tensors are skipped
+    assert type(plain) is PreparedBatch and plain.owners == ()
+    plain.record_stream(object())
+    assert pb.to("cpu").x.shape == (3, 4)
+
+
+def test_trace_label_table_matches_header():
+    """The label order of _lib.TRACE_LABELS is the enum order documented in the header."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "salient_b200.h")).read()
+    doc = text[text.index("diagnostics: event trace"):text.index("int spp_trace_begin")]
+    doc = doc[doc.index("issue order: label"):]
+    ids = [int(v) for v in re.findall(r"(?<![\w.])(\d+) [a-zA-Z]", doc)]
+    assert ids[:16] == list(range(16)) and len(_lib.TRACE_LABELS) == 16
+    cuh = open(os.path.join(root, "salient_plusplus_b200", "csrc", "common.cuh")).read()
+    enum = cuh[cuh.index("enum TraceLabel {"):cuh.index("};", cuh.index("enum TraceLabel {"))]
+    assert len(re.findall(r"kTr\w+", enum)) == len(_lib.TRACE_LABELS)
