@@ -1,12 +1,14 @@
-"""Host-side mirror of ``fast_trainer/samplers.py`` on top of the GPU ``fast_sampler`` module:
-``FastSamplerConfig`` (:271-305), ``FastSampler`` (:372-399), ``FastSamplerIter`` (:331-357),
-``ProtoDistributedBatch`` (:32-164), ``PreparedBatch`` (:213-268), ``ProtoBatch`` (:197-210),
-``FastSamplerStats`` (:308-328).  Same names, fields and iterator protocol, so the reference's
-``driver/`` and ``fast_trainer/train.py`` run on it unchanged."""
+"""Batch containers and the sampler front end the reference's training code talks to, on top of
+the GPU ``fast_sampler`` module.  The public names, fields and iterator protocol are those of
+``fast_trainer/samplers.py`` -- ``FastSamplerConfig`` (:271-305), ``FastSampler`` (:372-399),
+``FastSamplerIter`` (:331-357), ``ProtoDistributedBatch`` (:32-164), ``PreparedBatch`` (:213-268),
+``ProtoBatch`` (:197-210), ``FastSamplerStats`` (:308-328) -- so ``driver/`` and
+``fast_trainer/train.py`` run on it unchanged; the bodies are written for batches
+that are born in HBM (one arena per batch, ``owners``) rather than moved there."""
 from __future__ import annotations
 
+import dataclasses
 import datetime
-from dataclasses import dataclass, fields
 from typing import Iterable, Iterator, List, NamedTuple, Optional, Sized
 
 import torch
@@ -14,6 +16,34 @@ import torch
 from . import fast_sampler
 from .adj import Adj, Adj__from_fast_sampler
 from .fast_sampler import Cache, RangePartitionBook
+
+
+# ---- helpers shared by the containers -------------------------------------------------------------
+def _wrap(raw_adjs) -> List[Adj]:
+    """(rowptr, col, e_id, sizes) tuples of the sampler -> Adj records the models consume."""
+    return list(map(Adj__from_fast_sampler, raw_adjs))
+
+
+def _as_slice(rng) -> slice:
+    lo, hi = rng
+    return slice(lo, hi)
+
+
+def _mark(stream, owners, tensors=(), adjs=()):
+    """record_stream on the owning allocations when they are known, else on every device tensor."""
+    if owners:
+        for block in owners:
+            block.record_stream(stream)
+        return
+    for t in tensors:
+        if t is not None and t.is_cuda:
+            t.record_stream(stream)
+    for a in adjs:
+        a.record_stream(stream)
+
+
+def _flat_labels(y: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    return None if y is None else y.squeeze()
 
 
 class ProtoDistributedBatch(NamedTuple):
@@ -32,47 +62,29 @@ class ProtoDistributedBatch(NamedTuple):
 
     @classmethod
     def from_fast_sampler(cls, batch):
-        assert batch.sliced_cpu_features is not None
-        (start, stop) = batch.idx_range
-        return cls(partition_nids=batch.partition_nids, sliced_cpu_features=batch.sliced_cpu_features,
-                   sliced_cpu_labels=batch.sliced_cpu_labels, cached_nids=batch.cached_nids,
-                   perm_partition_to_mfg=batch.perm_partition_to_mfg,
-                   adjs=[Adj__from_fast_sampler(adj) for adj in batch.adjs], idx_range=slice(start, stop),
-                   n_id=getattr(batch, "n_id", None), x=getattr(batch, "x", None),
-                   owners=getattr(batch, "owners", ()))
+        if batch.sliced_cpu_features is None:
+            raise AssertionError("distributed batch without sliced_cpu_features")
+        return cls(batch.partition_nids, batch.sliced_cpu_features, batch.sliced_cpu_labels, batch.cached_nids,
+                   batch.perm_partition_to_mfg, _wrap(batch.adjs), _as_slice(batch.idx_range),
+                   getattr(batch, "n_id", None), getattr(batch, "x", None), getattr(batch, "owners", ()))
 
     def record_stream(self, stream):
-        if self.owners:
-            for t in self.owners:
-                t.record_stream(stream)
-            return
-        for part in self.partition_nids:
-            if part.is_cuda:
-                part.record_stream(stream)
-        if self.perm_partition_to_mfg.is_cuda:
-            self.perm_partition_to_mfg.record_stream(stream)
-        for adj in self.adjs:
-            adj.record_stream(stream)
-        for t in (self.n_id, self.x):
-            if t is not None and t.is_cuda:
-                t.record_stream(stream)
+        _mark(stream, self.owners, (*self.partition_nids, self.perm_partition_to_mfg, self.n_id, self.x), self.adjs)
 
     def to(self, device, stream=None, non_blocking=False, streams_to_sync=None, delay_feature_transfer=True):
+        def move(t):
+            return t.to(device, non_blocking=non_blocking)
+
         with torch.cuda.stream(stream):
-            mv = lambda t: t.to(device, non_blocking=non_blocking)
-            return self._replace(adjs=[adj.to(device, non_blocking=non_blocking) for adj in self.adjs],
-                                 partition_nids=[mv(p) for p in self.partition_nids],
-                                 perm_partition_to_mfg=mv(self.perm_partition_to_mfg),
-                                 sliced_cpu_features=(self.sliced_cpu_features if delay_feature_transfer
-                                                      else mv(self.sliced_cpu_features)))
+            moved = dict(partition_nids=list(map(move, self.partition_nids)),
+                         perm_partition_to_mfg=move(self.perm_partition_to_mfg),
+                         adjs=[a.to(device, non_blocking=non_blocking) for a in self.adjs])
+            if not delay_feature_transfer:
+                moved["sliced_cpu_features"] = move(self.sliced_cpu_features)
+            return self._replace(**moved)
 
-    @property
-    def num_total_nodes(self):
-        return self.perm_partition_to_mfg.size(0)
-
-    @property
-    def num_cached_nodes(self):
-        return self.cached_nids.size(0)
+    num_total_nodes = property(lambda self: self.perm_partition_to_mfg.size(0))
+    num_cached_nodes = property(lambda self: self.cached_nids.size(0))
 
 
 class ProtoBatch(NamedTuple):
@@ -82,12 +94,10 @@ class ProtoBatch(NamedTuple):
 
     @classmethod
     def from_fast_sampler(cls, proto_sample):
-        n_id, adjs, (start, stop) = proto_sample
-        return cls(n_id=n_id, adjs=[Adj__from_fast_sampler(adj) for adj in adjs], idx_range=slice(start, stop))
+        nodes, raw, rng = proto_sample
+        return cls(nodes, _wrap(raw), _as_slice(rng))
 
-    @property
-    def batch_size(self):
-        return self.idx_range.stop - self.idx_range.start
+    batch_size = property(lambda self: self.idx_range.stop - self.idx_range.start)
 
 
 class PreparedBatch(NamedTuple):
@@ -102,61 +112,48 @@ class PreparedBatch(NamedTuple):
 
     @classmethod
     def from_proto_batch(cls, x: torch.Tensor, y: Optional[torch.Tensor], proto_batch: ProtoBatch):
-        n_id = proto_batch.n_id
-        return cls(x=fast_sampler.serial_index(x, n_id),
-                   y=fast_sampler.serial_index(y.view(y.size(0), -1), n_id[:proto_batch.batch_size]).view(
-                       (-1,) + tuple(y.shape[1:])) if y is not None else None,
-                   adjs=proto_batch.adjs, idx_range=proto_batch.idx_range)
+        nodes = proto_batch.n_id
+        labels = None
+        if y is not None:  # labels of the seeds = the first batch_size entries of n_id
+            rows = fast_sampler.serial_index(y.view(y.size(0), -1), nodes[:proto_batch.batch_size])
+            labels = rows.view((-1,) + tuple(y.shape[1:]))
+        return cls(fast_sampler.serial_index(x, nodes), labels, proto_batch.adjs, proto_batch.idx_range)
 
     @classmethod
     def from_fast_sampler(cls, prepared_sample):
-        x, y, adjs, (start, stop) = prepared_sample
+        feats, labels, raw, rng = prepared_sample
         owners = getattr(prepared_sample, "owners", None)
-        if owners and cls is PreparedBatch:
-            b = OwnedPreparedBatch(x, y.squeeze() if y is not None else None,
-                                   [Adj__from_fast_sampler(adj) for adj in adjs], slice(start, stop))
-            b.owners = owners
-            return b
-        return cls(x=x, y=y.squeeze() if y is not None else None,
-                   adjs=[Adj__from_fast_sampler(adj) for adj in adjs], idx_range=slice(start, stop))
+        kind = OwnedPreparedBatch if (owners and cls is PreparedBatch) else cls
+        made = kind(feats, _flat_labels(labels), _wrap(raw), _as_slice(rng))
+        if kind is OwnedPreparedBatch:
+            made.owners = owners
+        return made
 
     def record_stream(self, stream):
-        if self.owners:
-            for t in self.owners:
-                t.record_stream(stream)
-            return
-        if self.x is not None and self.x.is_cuda:
-            self.x.record_stream(stream)
-        if self.y is not None and self.y.is_cuda:
-            self.y.record_stream(stream)
-        for adj in self.adjs:
-            adj.record_stream(stream)
+        _mark(stream, self.owners, (self.x, self.y), self.adjs)
 
     def to(self, device, non_blocking=False):
         # batches are born on the GPU: moving to the device they already live on is the identity
-        dev = torch.device(device)
-        if self.x is not None and self.x.is_cuda and dev.type == "cuda" and \
-                (dev.index is None or dev.index == self.x.device.index):
+        target = torch.device(device)
+        here = self.x.device if self.x is not None else None
+        if here is not None and here.type == "cuda" and target.type == "cuda" and target.index in (None, here.index):
             return self
-        return PreparedBatch(
-            x=self.x.to(device=device, non_blocking=non_blocking) if self.x is not None else None,
-            y=self.y.to(device=device, non_blocking=non_blocking) if self.y is not None else None,
-            adjs=[adj.to(device=device, non_blocking=non_blocking) for adj in self.adjs], idx_range=self.idx_range)
 
-    @property
-    def num_total_nodes(self):
-        return self.x.size(0)
+        def move(t):
+            return None if t is None else t.to(device=device, non_blocking=non_blocking)
 
-    @property
-    def batch_size(self):
-        return self.idx_range.stop - self.idx_range.start
+        return PreparedBatch(move(self.x), move(self.y),
+                             [a.to(device=device, non_blocking=non_blocking) for a in self.adjs], self.idx_range)
+
+    num_total_nodes = property(lambda self: self.x.size(0))
+    batch_size = property(lambda self: self.idx_range.stop - self.idx_range.start)
 
 
 class OwnedPreparedBatch(PreparedBatch):
     """A PreparedBatch (same four fields) that also carries ``owners`` as an instance attribute."""
 
 
-@dataclass
+@dataclasses.dataclass
 class FastSamplerConfig:
     x_cpu: torch.Tensor
     x_gpu: torch.Tensor
@@ -182,23 +179,23 @@ class FastSamplerConfig:
     fused_gather: bool = True
 
     def to_fast_sampler(self) -> fast_sampler.Config:
-        c = fast_sampler.Config()
-        for field in fields(self):
-            if not self.distributed and field.name == "partition_book":
-                continue
-            v = getattr(self, field.name)
-            if field.name == "cache" and v is None:
-                v = Cache()
-            setattr(c, field.name, v)
-        return c
+        """The module-level Config with the same field values (a partition book only travels for
+        distributed runs; a missing cache becomes the empty Cache the module expects)."""
+        native = fast_sampler.Config()
+        values = {f.name: getattr(self, f.name) for f in dataclasses.fields(self)}
+        if not self.distributed:
+            values.pop("partition_book")
+        if values["cache"] is None:
+            values["cache"] = Cache()
+        for name, value in values.items():
+            setattr(native, name, value)
+        return native
 
     def get_num_batches(self) -> int:
         if self.force_exact_num_batches:
             return self.exact_num_batches
-        num_batches, r = divmod(self.idx.numel(), self.batch_size)
-        if not self.skip_nonfull_batch and r > 0:
-            num_batches += 1
-        return num_batches
+        seeds, per = self.idx.numel(), self.batch_size
+        return seeds // per if self.skip_nonfull_batch else -(-seeds // per)
 
 
 class FastSamplerStats(NamedTuple):
@@ -207,8 +204,7 @@ class FastSamplerStats(NamedTuple):
 
     @classmethod
     def from_session(cls, session):
-        return cls(total_blocked_dur=session.total_blocked_dur,
-                   total_blocked_occasions=session.total_blocked_occasions)
+        return cls(session.total_blocked_dur, session.total_blocked_occasions)
 
 
 class FastSamplerDistributedStats(NamedTuple):
@@ -217,30 +213,30 @@ class FastSamplerDistributedStats(NamedTuple):
 
     @classmethod
     def from_session(cls, session):
-        assert session.num_consumed_batches == session.num_total_batches
+        if session.num_consumed_batches != session.num_total_batches:
+            raise AssertionError("remote-frequency statistics need a fully consumed Session")
         session.reduce_multithreaded_frequency_counts()
-        return cls(remote_frequency_tensor=session.remote_frequency_tensor,
-                   remote_vertices_ordered_by_freq=session.remote_vertices_ordered_by_freq)
+        return cls(session.remote_frequency_tensor, session.remote_vertices_ordered_by_freq)
 
 
 class FastSamplerIter(Iterator[PreparedBatch]):
     session: fast_sampler.Session
 
     def __init__(self, num_threads: int, max_items_in_queue: int, cfg: FastSamplerConfig):
-        ncfg = cfg.to_fast_sampler()
-        self.session = fast_sampler.Session(num_threads, max_items_in_queue, ncfg)
-        assert self.session.num_total_batches == cfg.get_num_batches()
+        self.session = fast_sampler.Session(num_threads, max_items_in_queue, cfg.to_fast_sampler())
+        if self.session.num_total_batches != cfg.get_num_batches():
+            raise AssertionError("Session and FastSamplerConfig disagree on the number of batches")
+        # one (fetch, wrap) pair per mode, chosen once
+        if self.session.config.distributed:
+            self._fetch, self._wrap = self.session.blocking_get_batch_distributed, ProtoDistributedBatch.from_fast_sampler
+        else:
+            self._fetch, self._wrap = self.session.blocking_get_batch, PreparedBatch.from_fast_sampler
 
     def __next__(self):
-        if not self.session.config.distributed:
-            sample = self.session.blocking_get_batch()
-            if sample is None:
-                raise StopIteration
-            return PreparedBatch.from_fast_sampler(sample)
-        sample = self.session.blocking_get_batch_distributed()
-        if sample is None:
+        got = self._fetch()
+        if got is None:
             raise StopIteration
-        return ProtoDistributedBatch.from_fast_sampler(sample)
+        return self._wrap(got)
 
     def get_stats(self) -> FastSamplerStats:
         return FastSamplerStats.from_session(self.session)
@@ -253,27 +249,19 @@ class ABCNeighborSampler(Iterable[PreparedBatch], Sized):
     pass
 
 
-@dataclass
+def _cfg_attr(name: str) -> property:
+    """Read/write pass-through to ``self.cfg.<name>`` (the driver swaps idx / cache between epochs)."""
+    return property(lambda self: getattr(self.cfg, name), lambda self, value: setattr(self.cfg, name, value))
+
+
+@dataclasses.dataclass
 class FastSampler(ABCNeighborSampler):
     num_threads: int
     max_items_in_queue: int
     cfg: FastSamplerConfig
 
-    @property
-    def idx(self):
-        return self.cfg.idx
-
-    @idx.setter
-    def idx(self, idx: torch.Tensor) -> None:
-        self.cfg.idx = idx
-
-    @property
-    def cache(self):
-        return self.cfg.cache
-
-    @cache.setter
-    def cache(self, cache: Cache) -> None:
-        self.cfg.cache = cache
+    idx = _cfg_attr("idx")
+    cache = _cfg_attr("cache")
 
     def __iter__(self):
         return FastSamplerIter(self.num_threads, self.max_items_in_queue, self.cfg)
