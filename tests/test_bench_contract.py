@@ -1,0 +1,30 @@
+"""bench.py contract checks that need no GPU: the reference arm (the reference's own CPU
+fast_sampler Session, oracle/_ref, or the C port) runs end to end at a tiny scale and prints the
+one JSON line the driver parses."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.01",
+                        "--steps", "3", "--warmup", "3"], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "sampled_and_gathered_minibatches_per_sec"
+    assert line["unit"] == "batches/s" and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["value"] > 0 and line["steps"] == 3 and line["warmup"] >= 3
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "batches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["config"]["workload"].startswith("ogbn-products-shaped")
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--scale",
+                        "0.01", "--steps", "3", "--warmup", "3"], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == ""
