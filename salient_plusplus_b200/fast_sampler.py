@@ -659,6 +659,29 @@ def _executor(device_index: int):
     return ex
 
 
+def _arena_cuts(lay, m: Sequence[int], L: int, P: Optional[int]) -> List[int]:
+    """Piece sizes that cut one batch's arena into its exact-size tensors with a single
+    ``split_with_sizes``.  ``lay`` = Session._layout(...), ``m`` = host copy of the size block
+    (meta words, then the owner-split counts), ``P`` = partitions (None: not distributed).
+    Pieces: per hop ``[rowptr (T+1) | slack | col (E) | slack]`` -> indices 4h and 4h+2; then,
+    distributed, ``[n_id | slack | P partition buckets | cached | slack | perm | slack | tail]``
+    starting at index 4L, else one tail piece."""
+    a_off, a_nid, _, a_words, mx = lay
+    cuts: List[int] = []
+    for h in range(L):
+        ro, co = a_off[h]
+        T, E = m[h], m[META_EDGES0 + h]
+        end = a_off[h + 1][0] if h + 1 < L else a_nid
+        cuts += [T + 1, co - ro - T - 1, E, end - co - E]
+    if P is None:
+        cuts.append(a_words - a_nid)
+    else:
+        counts = list(m[SPP_META_WORDS:SPP_META_WORDS + P + 1])
+        nb = m[L]
+        cuts += [nb, mx - nb] + counts + [mx - sum(counts), nb, mx - nb, a_words - a_nid - 3 * mx]
+    return cuts
+
+
 _SLOT_POOL: dict = {}
 _EMPTY_EID: dict = {}
 
@@ -1111,21 +1134,7 @@ class Session:
             arena, e_id = job["arena"], _empty_eid(self._device)
             # every exact-size view of the structure part of the arena in ONE split call: per hop
             # [rowptr | slack | col | slack] (the slack pieces are dropped)
-            a_off, a_nid, _, a_words, mx = job["lay"]
-            cuts = []
-            for h in range(L):
-                ro, co = a_off[h]
-                T, E = m[h], m[META_EDGES0 + h]
-                end = a_off[h + 1][0] if h + 1 < L else a_nid
-                cuts += [T + 1, co - ro - T - 1, E, end - co - E]
-            if cfg.distributed:  # n_id | bucketed ids (P partitions, cached) | perm, each `mx` wide
-                counts = m[SPP_META_WORDS:]
-                P, nb_ = self._P, m[L]
-                used = sum(counts[:P + 1])
-                cuts += [nb_, mx - nb_] + counts[:P + 1] + [mx - used, nb_, mx - nb_, a_words - a_nid - 3 * mx]
-            else:
-                cuts.append(a_words - a_nid)
-            v = arena.split_with_sizes(cuts)
+            v = arena.split_with_sizes(_arena_cuts(job["lay"], m, L, self._P if cfg.distributed else None))
             adjs = [(v[4 * h], v[4 * h + 2], e_id, (m[h], m[h + 1])) for h in range(L - 1, -1, -1)]  # reversed like fast_sampler.cpp:224
             nb = m[L]
         start, stop = job["range"]

@@ -113,3 +113,36 @@ def test_trace_label_table_matches_header():
     cuh = open(os.path.join(root, "salient_plusplus_b200", "csrc", "common.cuh")).read()
     enum = cuh[cuh.index("enum TraceLabel {"):cuh.index("};", cuh.index("enum TraceLabel {"))]
     assert len(re.findall(r"kTr\w+", enum)) == len(_lib.TRACE_LABELS)
+
+
+def test_arena_cuts_cover_the_arena_and_land_on_the_layout():
+    """One split call cuts a batch's arena: the pieces must tile the arena exactly and the
+    tensors must start at the offsets the kernels were given."""
+    from salient_plusplus_b200._lib import META_EDGES0, SPP_META_WORDS
+    from salient_plusplus_b200.fast_sampler import _arena_cuts
+    # layout of a 2-hop batch: bounds T=(4, 10), E=(12, 30), node bound 40, 3 label words at the tail
+    a_off = [(0, 5), (17, 28)]
+    a_nid = 58
+    m = [0] * (SPP_META_WORDS + 18)
+    m[0], m[1], m[2] = 4, 9, 21                       # |n_id| before hop 0 / 1, final
+    m[META_EDGES0], m[META_EDGES0 + 1] = 7, 25
+    # non-distributed
+    lay = (a_off, a_nid, a_nid, a_nid + 3, 40)
+    cuts = _arena_cuts(lay, m, 2, None)
+    assert sum(cuts) == lay[3] and all(c >= 0 for c in cuts)
+    starts = [sum(cuts[:i]) for i in range(len(cuts))]
+    assert (starts[0], cuts[0]) == (0, 5) and (starts[2], cuts[2]) == (5, 7)          # hop 0 rowptr, col
+    assert (starts[4], cuts[4]) == (17, 10) and (starts[6], cuts[6]) == (28, 25)      # hop 1 rowptr, col
+    # distributed, P = 3: buckets 6 + 5 + 4, 6 cached
+    m[SPP_META_WORDS:SPP_META_WORDS + 4] = [6, 5, 4, 6]
+    lay = (a_off, a_nid, a_nid + 120, a_nid + 123, 40)
+    cuts = _arena_cuts(lay, m, 2, 3)
+    assert sum(cuts) == lay[3] and all(c >= 0 for c in cuts)
+    starts = [sum(cuts[:i]) for i in range(len(cuts))]
+    q = 8
+    assert (starts[q], cuts[q]) == (58, 21)                                           # n_id
+    assert [starts[q + 2 + p] for p in range(3)] == [98, 104, 109] and cuts[q + 2:q + 5] == [6, 5, 4]
+    assert (starts[q + 5], cuts[q + 5]) == (113, 6)                                   # cached ids
+    assert (starts[q + 7], cuts[q + 7]) == (138, 21)                                  # perm
+    t = torch.arange(lay[3]).split_with_sizes(cuts)
+    assert t[q + 7][0].item() == 138 and t[-1].numel() == 3
