@@ -28,3 +28,15 @@ def test_reference_arm_other_ranks_exit_quietly():
                         "0.01", "--steps", "3", "--warmup", "3"], cwd=ROOT, env=env, capture_output=True, text=True,
                        timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_tools_and_entry_points_compile():
+    """Every helper script must at least byte-compile (they only run on the GPU box)."""
+    import glob
+    import py_compile
+    paths = glob.glob(os.path.join(ROOT, "tools", "*.py")) + [os.path.join(ROOT, "bench.py"),
+                                                              os.path.join(ROOT, "__graft_entry__.py"),
+                                                              os.path.join(ROOT, "tests", "multigpu_check.py")]
+    assert len(paths) >= 8
+    for p in paths:
+        py_compile.compile(p, doraise=True)
