@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPP_ABI_VERSION 1
+#define SPP_ABI_VERSION 2
 #define SPP_MAX_PARTS 16   /* partitions in a RangePartitionBook                               */
 #define SPP_MAX_HOPS 8     /* hops per mini-batch                                              */
 #define SPP_MAX_FANOUT 128 /* without-replacement fanout per hop (full neighbourhood: no cap)  */
@@ -74,23 +74,33 @@ typedef struct spp_feature_map {
                                         /* GPU's HBM mapped through CUDA IPC); may be NULL for */
                                         /* partitions this GPU cannot reach                    */
   const void* cache_table;              /* cached_features [C, F] or NULL                      */
-  const int32_t* cache_map;             /* dense int32[N]: cache row of a node id, -1 if none  */
-                                        /* (the reference keeps a dense map too,               */
-                                        /*  range_partition_book.cpp:152-158); NULL = no cache */
+  const void* cache_index;              /* membership + rank index over the node ids, built by */
+                                        /* spp_cache_build_index (replaces the reference's     */
+                                        /* dense arrays, range_partition_book.cpp:152-158);    */
+                                        /* NULL = no cache                                     */
+  int64_t cache_index_nodes;            /* num_nodes the index was built for                   */
   int64_t table_pitch;                  /* byte pitch of tables[*] rows; 0 = dense (row_bytes) */
   int64_t cache_pitch;                  /* byte pitch of cache_table rows; 0 = dense           */
+  uint32_t local_parts;                 /* bit p set: partition p is resident on THIS GPU as   */
+                                        /* well (a GPU hosting several partitions when there   */
+                                        /* are fewer GPUs than partitions); bit `rank` implied */
+  uint32_t _pad;
 } spp_feature_map;
 
 /* K4+K5 -- fused partition-book translate + cache lookup + local/cached gather + P2P miss
  * fetch, written ONCE in MFG (n_id) order.  Replaces stages slicing1..4, the three
  * all_to_alls and combine_features of fast_trainer/transferers.py:462-766:
  *   p = nid2partid(n_id[i]);  row = p == rank ? tables[rank][n_id[i]-off[rank]]
- *                                  : cached(n_id[i]) ? cache_table[cache_map[n_id[i]]]
+ *                                  : cached(n_id[i]) ? cache_table[nid2cachenid(n_id[i])]
  *                                  : tables[p][n_id[i]-off[p]]           (peer HBM over NVLink)
+ * src_desc (optional, int32[n]): the per-node source descriptors spp_split_by_owner left in
+ *   scratch[0..n) for the SAME n_id list (p >= 0: partition p, < 0: ~cache row); the kernel then
+ *   reads them sequentially instead of searching the book and probing the cache index.
  * counters (optional, int64[3]): rows served local / cache / peer are ADDED to it. */
 int spp_gather_partitioned(const spp_feature_map* map_host, int64_t row_bytes, const void* n_id,
-                           int idx_is_64, int64_t n_idx, const int64_t* n_idx_dev, void* out,
-                           int64_t n_out_rows, int64_t* counters, void* stream);
+                           int idx_is_64, int64_t n_idx, const int64_t* n_idx_dev,
+                           const int32_t* src_desc, void* out, int64_t n_out_rows,
+                           int64_t* counters, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2 -- RangePartitionBook kernels (fast_sampler/range_partition_book.cpp:89-107).
@@ -105,17 +115,23 @@ int spp_nid2localnid(const int64_t* offsets_host, int num_parts, int partition_i
 int spp_nid_is_local(const int64_t* offsets_host, int num_parts, int rank, const int64_t* nids,
                      int64_t n, uint8_t* out, void* stream);
 
-/* Cache (fast_sampler/range_partition_book.cpp:116-195) */
-/* cache_map[v] = -1 for all v < num_nodes, then cache_map[cached_vertices[i]] = i (the largest
- * i wins for a duplicated vertex, like the reference's sequential overwrite :154-158) */
-int spp_cache_build_map(const int64_t* cached_vertices, int64_t n_cached, int32_t* cache_map,
-                        int64_t num_nodes, void* stream);
-/* out[i] = cache_map[nids[i]] >= 0   (bool bytes) */
-int spp_nid_is_cached(const int32_t* cache_map, const int64_t* nids, int64_t n, uint8_t* out,
-                      void* stream);
-/* out[i] = cache_map[nids[i]]   (int64) */
-int spp_nid2cachenid(const int32_t* cache_map, const int64_t* nids, int64_t n, int64_t* out,
-                     void* stream);
+/* Cache (fast_sampler/range_partition_book.cpp:116-195).  The reference keeps two dense host
+ * arrays indexed by node id (bool cached[200M], int32 row[200M]); a random probe of a dense map
+ * that size costs a DRAM access, three times per remote node and mini-batch.  Here the lookup
+ * structure is an L2-resident index: one 32-byte block per 224 ids holding the membership bits
+ * and the number of cached ids in front of the block, plus rank -> cache row (int32 per cached
+ * vertex).  index must hold spp_cache_index_bytes(num_nodes, n_cached) bytes (256-byte aligned).
+ * A vertex listed twice maps to its LAST position, like the reference's sequential overwrite
+ * (:154-158); ids outside [0, num_nodes) are ignored. */
+int64_t spp_cache_index_bytes(int64_t num_nodes, int64_t n_cached);
+int spp_cache_build_index(const int64_t* cached_vertices, int64_t n_cached, int64_t num_nodes,
+                          void* index, void* stream);
+/* out[i] = nids[i] is cached   (bool bytes) */
+int spp_nid_is_cached(const void* index, int64_t num_nodes, const int64_t* nids, int64_t n,
+                      uint8_t* out, void* stream);
+/* out[i] = cache row of nids[i], -1 if not cached   (int64) */
+int spp_nid2cachenid(const void* index, int64_t num_nodes, const int64_t* nids, int64_t n,
+                     int64_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3 -- distributed split of a mini-batch's node list (fast_sampler/fast_sampler.cpp:1017-1262).
@@ -128,7 +144,9 @@ int spp_nid2cachenid(const int32_t* cache_map, const int64_t* nids, int64_t n, i
  *   bucket_counts[b] = size of bucket b     (int64[P+1]); bucket_counts[P+1] = n
  * use_cache == 0 reproduces the no-cache branch (:1031-1107).
  * n_dev (optional): take n from device memory (upper bound n_max sizes the grid).
- * scratch: int32[spp_split_scratch_words(n_max)] device words.
+ * scratch: int32[spp_split_scratch_words(n_max)] device words; on return scratch[0..n) holds the
+ *   per-node source descriptor (p >= 0: fetched from partition p, < 0: ~cache row) that
+ *   spp_gather_partitioned accepts as src_desc -- the cache index is probed once per node.
  * ---------------------------------------------------------------------------------------- */
 int64_t spp_split_scratch_words(int64_t n_max);
 int spp_split_by_owner(const spp_feature_map* map_host, int use_cache, const void* n_id,
@@ -282,6 +300,7 @@ typedef struct spp_batch_job {
   int32_t* split_scratch;
   int64_t* meta_host;              /* pinned int64[SPP_META_WORDS + SPP_MAX_PARTS + 2] or NULL  */
   void* stream;
+  int64_t* gather_counters;        /* optional device int64[3]: rows served local / cache / peer */
 } spp_batch_job;
 
 /* issue every call of the job on the calling thread (asynchronous w.r.t. the GPU) */

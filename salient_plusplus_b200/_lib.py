@@ -16,6 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsalient_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
+ABI_VERSION = 2
 SPP_MAX_PARTS = 16
 SPP_MAX_HOPS = 8
 SPP_MAX_FANOUT = 128
@@ -27,7 +28,7 @@ EXPORTED = [
     "spp_abi_version", "spp_last_error", "spp_launch_count",
     "spp_gather_rows", "spp_gather_rows_pitched", "spp_gather_partitioned",
     "spp_nid2partid", "spp_nid2localnid", "spp_nid_is_local",
-    "spp_cache_build_map", "spp_nid_is_cached", "spp_nid2cachenid",
+    "spp_cache_index_bytes", "spp_cache_build_index", "spp_nid_is_cached", "spp_nid2cachenid",
     "spp_split_scratch_words", "spp_split_by_owner",
     "spp_sampler_sizes", "spp_sample_minibatch", "spp_sample_begin", "spp_sample_hop_count",
     "spp_sample_hop_fill", "spp_sample_export_nids", "spp_debug_set_timeline",
@@ -43,8 +44,9 @@ class FeatureMap(Structure):
     _fields_ = [("num_parts", c_int32), ("rank", c_int32),
                 ("offsets", c_int64 * (SPP_MAX_PARTS + 1)),
                 ("tables", c_void_p * SPP_MAX_PARTS),
-                ("cache_table", c_void_p), ("cache_map", c_void_p),
-                ("table_pitch", c_int64), ("cache_pitch", c_int64)]
+                ("cache_table", c_void_p), ("cache_index", c_void_p), ("cache_index_nodes", c_int64),
+                ("table_pitch", c_int64), ("cache_pitch", c_int64),
+                ("local_parts", ctypes.c_uint32), ("_pad", ctypes.c_uint32)]
 
 
 class Graph(Structure):
@@ -78,7 +80,8 @@ class BatchJob(Structure):
                 ("table", c_void_p), ("table_pitch", c_int64), ("row_bytes", c_int64),
                 ("fmap", FeatureMap), ("x_out", c_void_p), ("y_table", c_void_p), ("y_row_bytes", c_int64),
                 ("y_out", c_void_p), ("bucket_ids", c_void_p), ("perm", c_void_p), ("bucket_counts", c_void_p),
-                ("split_scratch", c_void_p), ("meta_host", c_void_p), ("stream", c_void_p)]
+                ("split_scratch", c_void_p), ("meta_host", c_void_p), ("stream", c_void_p),
+                ("gather_counters", c_void_p)]
 
 
 class SalientB200Error(RuntimeError):
@@ -113,13 +116,15 @@ def load() -> ctypes.CDLL:
     L.spp_launch_count.restype = c_uint64
     L.spp_gather_rows.argtypes = [vp, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_rows_pitched.argtypes = [vp, i64, i64, vp, ci, i64, vp, vp, i64, vp]
-    L.spp_gather_partitioned.argtypes = [POINTER(FeatureMap), i64, vp, ci, i64, vp, vp, i64, vp, vp]
+    L.spp_gather_partitioned.argtypes = [POINTER(FeatureMap), i64, vp, ci, i64, vp, vp, vp, i64, vp, vp]
     L.spp_nid2partid.argtypes = [POINTER(i64), ci, vp, i64, vp, vp]
     L.spp_nid2localnid.argtypes = [POINTER(i64), ci, ci, vp, i64, vp, vp]
     L.spp_nid_is_local.argtypes = [POINTER(i64), ci, ci, vp, i64, vp, vp]
-    L.spp_cache_build_map.argtypes = [vp, i64, vp, i64, vp]
-    L.spp_nid_is_cached.argtypes = [vp, vp, i64, vp, vp]
-    L.spp_nid2cachenid.argtypes = [vp, vp, i64, vp, vp]
+    L.spp_cache_index_bytes.restype = i64
+    L.spp_cache_index_bytes.argtypes = [i64, i64]
+    L.spp_cache_build_index.argtypes = [vp, i64, i64, vp, vp]
+    L.spp_nid_is_cached.argtypes = [vp, i64, vp, i64, vp, vp]
+    L.spp_nid2cachenid.argtypes = [vp, i64, vp, i64, vp, vp]
     L.spp_split_scratch_words.restype = i64
     L.spp_split_scratch_words.argtypes = [i64]
     L.spp_split_by_owner.argtypes = [POINTER(FeatureMap), ci, vp, ci, i64, vp, vp, vp, vp, vp, vp]
@@ -156,7 +161,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(L, name)  # raises AttributeError if a declared symbol is not exported
         if fn.restype is ci and name not in ("spp_abi_version",):
             pass
-    if L.spp_abi_version() != 1:
+    if L.spp_abi_version() != ABI_VERSION:
         raise SalientB200Error("libsalient_b200.so ABI version mismatch")
     _lib = L
     return L

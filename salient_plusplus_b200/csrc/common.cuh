@@ -150,12 +150,92 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
   return v;
 }
 
+// ---- L2 eviction-priority hints ---------------------------------------------------------------
+// The 126 MB L2 is shared by streams of feature rows that are touched once (hundreds of MB per
+// mini-batch) and by small random-access structures that every mini-batch probes again (the cache
+// index below, 16-35 MB).  Rows are streamed with evict_first, the index is read with evict_last,
+// so the index stays resident instead of costing a DRAM line per probe.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld_l2hint(const uint4* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_l2hint(const uint32_t* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+
+// ---- cache index (replaces the reference's dense id -> cache-row arrays,
+//      fast_sampler/range_partition_book.cpp:152-158) ------------------------------------------
+// One 32-byte block (= one L2 sector) per 224 node ids: word 0 = number of cached ids in all
+// earlier blocks, words 1..7 = membership bits.  A probe is ONE sector read: membership, and for a
+// member its rank among the cached ids in ascending id order; rank2row[rank] is the row of the
+// reference's cached_features.  N/7 bytes (papers100M: 15.9 MB, MAG240M: 34.9 MB) instead of a
+// 4N-byte dense map (444 / 976 MB) whose random probes each cost a DRAM access.
+constexpr uint32_t kCacheBlockIds = 224;
+struct CacheIndex {
+  const uint4* blocks;      // [ceil(nodes / 224)][2]
+  const int32_t* rank2row;  // [number of distinct cached ids]
+  int64_t nodes;            // ids >= nodes are not cached
+};
+__host__ __device__ __forceinline__ int64_t cache_index_blocks(int64_t nodes) {
+  return (nodes + kCacheBlockIds - 1) / kCacheBlockIds;
+}
+__host__ __device__ __forceinline__ CacheIndex make_cache_index(const void* base, int64_t nodes) {
+  CacheIndex c;
+  c.blocks = reinterpret_cast<const uint4*>(base);
+  c.rank2row = reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(base) + cache_index_blocks(nodes) * 32);
+  c.nodes = base ? nodes : 0;
+  return c;
+}
+// rank of `id` among the cached ids, or -1
+__device__ __forceinline__ int32_t cache_rank(const CacheIndex& c, int64_t id, uint64_t pol) {
+  if (id < 0 || id >= c.nodes) return -1;
+  const uint32_t u = (uint32_t)id;
+  const uint32_t blk = u / kCacheBlockIds, bit = u - blk * kCacheBlockIds;
+  const uint4* b = c.blocks + 2 * (size_t)blk;
+  const uint4 lo = ld_l2hint(b, pol), hi = ld_l2hint(b + 1, pol);
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  const uint32_t wi = (bit >> 5) + 1u, m = 1u << (bit & 31u);
+  uint32_t rank = w[0];
+  bool hit = false;
+#pragma unroll
+  for (uint32_t q = 1; q < 8; ++q) {
+    if (q < wi) rank += __popc(w[q]);
+    else if (q == wi) {
+      hit = (w[q] & m) != 0u;
+      rank += __popc(w[q] & (m - 1u));
+    }
+  }
+  return hit ? (int32_t)rank : -1;
+}
+// row of cached_features holding `id`, or -1
+__device__ __forceinline__ int32_t cache_lookup(const CacheIndex& c, int64_t id, uint64_t pol) {
+  const int32_t r = cache_rank(c, id, pol);
+  return r < 0 ? -1 : (int32_t)ld_l2hint(reinterpret_cast<const uint32_t*>(c.rank2row) + r, pol);
+}
+
 // Range partition book in kernel-parameter space (<= 17 offsets: a register-resident search)
 struct BookParams {
   int64_t off[SPP_MAX_PARTS + 1];
   int num_parts;
   int rank;
+  uint32_t local_mask;  // bit p: partition p is resident on this GPU (always includes `rank`)
 };
+__device__ __forceinline__ bool book_is_local(const BookParams& b, int p) { return (b.local_mask >> p) & 1u; }
 // searchsorted(off, nid, right=True) - 1, clamped like the reference's use (ids inside [0, N))
 __device__ __forceinline__ int book_partid(const BookParams& b, int64_t nid) {
   int p = 0;

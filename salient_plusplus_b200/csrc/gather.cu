@@ -35,7 +35,9 @@ struct GatherParams {
   BookParams book;
   const char* tables[SPP_MAX_PARTS];
   const char* cache_table;
-  const int32_t* cache_map;
+  CacheIndex cache;              // cache.nodes == 0: no cache
+  const int32_t* desc;           // optional per-row source descriptors written by spp_split_by_owner
+                                 // (p >= 0: partition p, < 0: ~cache row): no book search, no probe
   unsigned long long* counters;  // [3] local / cache / peer rows (optional)
 };
 
@@ -48,12 +50,22 @@ struct RowResolver {
   int32_t crow = -1;   // cache row (in flight until `finish`)
   bool on = false;
 
-  __device__ __forceinline__ void begin_lookup(const GatherParams& prm) {
+  __device__ __forceinline__ void begin_lookup(const GatherParams& prm, int64_t row, uint64_t pol) {
     if constexpr (kPartitioned) {
       crow = -1;
       if (on) {
-        p = book_partid(prm.book, id);
-        if (p != prm.book.rank && prm.cache_map != nullptr) crow = __ldg(prm.cache_map + id);
+        if (prm.desc != nullptr) {
+          const int32_t d = __ldg(prm.desc + row);
+          if (d < 0) {
+            crow = ~d;
+            p = -1;
+          } else {
+            p = d;
+          }
+        } else {
+          p = book_partid(prm.book, id);
+          if (!book_is_local(prm.book, p) && prm.cache.nodes > 0) crow = cache_lookup(prm.cache, id, pol);
+        }
       }
     }
   }
@@ -64,13 +76,13 @@ struct RowResolver {
     if constexpr (!kPartitioned) {
       return prm.table + id * prm.table_pitch;
     } else {
-      if (p == prm.book.rank) {
-        cls = 0;
-        return prm.tables[p] + (id - prm.book.off[p]) * prm.table_pitch;
-      }
       if (crow >= 0) {
         cls = 1;
         return prm.cache_table + (int64_t)crow * prm.cache_pitch;
+      }
+      if (book_is_local(prm.book, p)) {
+        cls = 0;
+        return prm.tables[p] + (id - prm.book.off[p]) * prm.table_pitch;
       }
       cls = 2;
       return prm.tables[p] + (id - prm.book.off[p]) * prm.table_pitch;  // peer HBM over NVLink
@@ -92,6 +104,8 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
   const uint32_t vpr = prm.vpr, magic = prm.vpr_magic;
   const bool resolver = tid < kRows;  // warps 0 and 1
   unsigned long long cnt0 = 0, cnt1 = 0, cnt2 = 0;
+  uint64_t pol = 0;
+  if constexpr (kPartitioned) pol = l2_policy_evict_last();
 
   auto load_id = [&](int64_t tile, RowResolver<kPartitioned>& r) {
     r.on = false;
@@ -129,7 +143,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
     RowResolver<kPartitioned> r0;
     load_id(tile, r0);
     load_id(tile + gridDim.x, r1);
-    r0.begin_lookup(prm);
+    r0.begin_lookup(prm, tile * kRows + tid, pol);
     publish(r0, 0);
   }
   __syncthreads();
@@ -138,7 +152,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
     const int64_t row0 = tile * kRows;
     const int rows = (int)((n - row0) < kRows ? (n - row0) : kRows);
     if (resolver) {
-      r1.begin_lookup(prm);                       // tile t+1: id arrived a tile ago
+      r1.begin_lookup(prm, (tile + gridDim.x) * kRows + tid, pol);  // tile t+1: id arrived a tile ago
       load_id(tile + 2 * (int64_t)gridDim.x, r2);  // tile t+2: id load in flight
     }
     const uint32_t chunks = (uint32_t)rows * vpr;
@@ -273,8 +287,8 @@ int spp_gather_rows_pitched(const void* table, int64_t table_pitch, int64_t row_
 }
 
 int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const void* n_id, int idx_is_64,
-                           int64_t n_idx, const int64_t* n_idx_dev, void* out, int64_t n_out_rows,
-                           int64_t* counters, void* stream) {
+                           int64_t n_idx, const int64_t* n_idx_dev, const int32_t* src_desc, void* out,
+                           int64_t n_out_rows, int64_t* counters, void* stream) {
   using namespace spp;
   if (!m) return fail(SPP_EINVAL, "spp_gather_partitioned: null feature map");
   if (m->num_parts < 1 || m->num_parts > SPP_MAX_PARTS || m->rank < 0 || m->rank >= m->num_parts)
@@ -283,8 +297,8 @@ int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const vo
   int64_t n = n_idx < n_out_rows ? n_idx : n_out_rows;
   if (n <= 0) return 0;
   if (!n_id || !out) return fail(SPP_EINVAL, "spp_gather_partitioned: null pointer");
-  if ((m->cache_map == nullptr) != (m->cache_table == nullptr))
-    return fail(SPP_EINVAL, "spp_gather_partitioned: cache_map and cache_table must be given together");
+  if ((m->cache_index == nullptr) != (m->cache_table == nullptr))
+    return fail(SPP_EINVAL, "spp_gather_partitioned: cache_index and cache_table must be given together");
   GatherParams prm{};
   prm.idx = n_id;
   prm.n_dev = n_idx_dev;
@@ -301,13 +315,15 @@ int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const vo
   for (int p = 0; p <= SPP_MAX_PARTS; ++p) prm.book.off[p] = p <= m->num_parts ? m->offsets[p] : m->offsets[m->num_parts];
   for (int p = 0; p < m->num_parts; ++p) {
     if (m->offsets[p + 1] < m->offsets[p]) return fail(SPP_EINVAL, "spp_gather_partitioned: offsets not sorted");
-    if (m->tables[p] == nullptr && m->offsets[p + 1] > m->offsets[p] && !(m->cache_map && p != m->rank))
+    if (m->tables[p] == nullptr && m->offsets[p + 1] > m->offsets[p] && !(m->cache_index && p != m->rank))
       return fail(SPP_EINVAL, "spp_gather_partitioned: partition %d has no table", p);
     prm.tables[p] = (const char*)m->tables[p];
     align |= (uintptr_t)m->tables[p];
   }
   prm.cache_table = (const char*)m->cache_table;
-  prm.cache_map = m->cache_map;
+  prm.cache = make_cache_index(m->cache_index, m->cache_index_nodes);
+  prm.desc = src_desc;
+  prm.book.local_mask = (1u << m->rank) | m->local_parts;
   align |= (uintptr_t)m->cache_table;
   prm.counters = (unsigned long long*)counters;
   int vb = pick_vec_bytes(row_bytes, align);

@@ -21,6 +21,7 @@ static int fill_book(BookParams& b, const int64_t* offsets, int num_parts, int r
   for (int p = 0; p <= SPP_MAX_PARTS; ++p) b.off[p] = offsets[p <= num_parts ? p : num_parts];
   b.num_parts = num_parts;
   b.rank = rank;
+  b.local_mask = (rank >= 0 && rank < num_parts) ? (1u << rank) : 0u;
   return 0;
 }
 
@@ -52,28 +53,95 @@ __global__ void k_nid_is_local(int64_t lo, int64_t hi, const int64_t* __restrict
   }
 }
 
-__global__ void k_fill_i32(int32_t* __restrict__ p, int64_t n, int32_t v) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
-}
+// ---- cache index construction (set-up time) ----------------------------------------------------
+// index buffer: [blocks: nblocks x 32 B][rank2row: int32 x n_cached][scan scratch: uint32 x (nblocks/256 + 1)]
+constexpr int kIdxThreads = 256;
 
-__global__ void k_cache_scatter(const int64_t* __restrict__ cached, int64_t n, int32_t* __restrict__ map,
-                                int64_t num_nodes) {
+__global__ void k_cache_setbits(const int64_t* __restrict__ cached, int64_t n, uint32_t* __restrict__ blocks, int64_t num_nodes) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = cached[i];
-    if (v >= 0 && v < num_nodes) atomicMax(map + v, (int32_t)i);
+    if (v >= 0 && v < num_nodes) {
+      const uint32_t u = (uint32_t)v, blk = u / kCacheBlockIds, bit = u - blk * kCacheBlockIds;
+      atomicOr(blocks + 8 * (size_t)blk + 1 + (bit >> 5), 1u << (bit & 31u));
+    }
   }
 }
 
-__global__ void k_nid_is_cached(const int32_t* __restrict__ map, const int64_t* __restrict__ nids, int64_t n,
-                                uint8_t* __restrict__ out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = __ldg(map + nids[i]) >= 0 ? 1 : 0;
+// per CTA of 256 blocks: popcount of every block -> exclusive scan inside the CTA -> word 0; CTA total -> sums
+__global__ void __launch_bounds__(kIdxThreads) k_cache_block_counts(uint32_t* __restrict__ blocks, int64_t nblocks,
+                                                                     uint32_t* __restrict__ sums) {
+  __shared__ uint32_t s_w[kIdxThreads / 32];
+  const int64_t b = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
+  uint32_t cnt = 0;
+  if (b < nblocks) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) cnt += __popc(blocks[8 * (size_t)b + q]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t inc = warp_incl_scan(cnt, lane);
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kIdxThreads / 32; ++w) {
+    if (w < warp) base += s_w[w];
+    total += s_w[w];
+  }
+  if (b < nblocks) blocks[8 * (size_t)b] = base + inc - cnt;
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
 
-__global__ void k_nid2cachenid(const int32_t* __restrict__ map, const int64_t* __restrict__ nids, int64_t n,
-                               int64_t* __restrict__ out) {
+// one CTA: exclusive scan of the per-CTA totals (<= a few thousand entries)
+__global__ void __launch_bounds__(1024) k_cache_scan_sums(uint32_t* __restrict__ sums, int64_t n) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (int64_t i0 = 0; i0 < n; i0 += 1024) {
+    const int64_t i = i0 + threadIdx.x;
+    const uint32_t v = i < n ? sums[i] : 0u;
+    const uint32_t inc = warp_incl_scan(v, lane);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t base = s_run, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) base += s_w[w];
+      total += s_w[w];
+    }
+    if (i < n) sums[i] = base + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) s_run += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kIdxThreads) k_cache_add_base(uint32_t* __restrict__ blocks, int64_t nblocks,
+                                                                 const uint32_t* __restrict__ sums) {
+  const int64_t b = (int64_t)blockIdx.x * kIdxThreads + threadIdx.x;
+  if (b < nblocks) blocks[8 * (size_t)b] += sums[blockIdx.x];
+}
+
+// rank2row[rank(v)] = largest i with cached[i] == v (the reference's sequential overwrite keeps the
+// last duplicate, range_partition_book.cpp:154-158)
+__global__ void k_cache_rank2row(const int64_t* __restrict__ cached, int64_t n, CacheIndex idx, int32_t* __restrict__ rank2row) {
+  const uint64_t pol = l2_policy_evict_last();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t r = cache_rank(idx, cached[i], pol);
+    if (r >= 0) atomicMax(rank2row + r, (int32_t)i);
+  }
+}
+
+__global__ void k_nid_is_cached(CacheIndex idx, const int64_t* __restrict__ nids, int64_t n, uint8_t* __restrict__ out) {
+  const uint64_t pol = l2_policy_evict_last();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = (int64_t)__ldg(map + nids[i]);
+    out[i] = cache_rank(idx, nids[i], pol) >= 0 ? 1 : 0;
+}
+
+__global__ void k_nid2cachenid(CacheIndex idx, const int64_t* __restrict__ nids, int64_t n, int64_t* __restrict__ out) {
+  const uint64_t pol = l2_policy_evict_last();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int64_t)cache_lookup(idx, nids[i], pol);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -89,13 +157,13 @@ struct SplitParams {
   const void* n_id;
   const int64_t* n_dev;
   int64_t n_max;
-  const int32_t* cache_map;  // NULL when the cache is not used
+  CacheIndex cache;  // cache.nodes == 0 when the cache is not used
   int64_t* bucket_ids;
   int64_t* perm;
   int64_t* bucket_counts;
   uint32_t* tile_hist;   // [tiles_max][kClasses] -> exclusive per-class prefix over tiles
   uint32_t* class_start; // [kClasses + 1]
-  uint8_t* cls;          // [n_max]
+  int32_t* desc;         // [n_max] per-node source descriptor: p >= 0 -> partition p, < 0 -> ~cache row
   int64_t tiles_max;
 };
 
@@ -114,6 +182,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_hist(const __grid_const
   const int64_t n = split_n(prm);
   const IdxT* __restrict__ ids = reinterpret_cast<const IdxT*>(prm.n_id);
   const int P = prm.book.num_parts;
+  const uint64_t pol = l2_policy_evict_last();
   for (int64_t tile = blockIdx.x; tile < prm.tiles_max; tile += gridDim.x) {
     if (threadIdx.x < kClasses) s_hist[threadIdx.x] = 0;
     __syncthreads();
@@ -124,8 +193,16 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_hist(const __grid_const
       if (i < n) {
         const int64_t nid = (int64_t)ids[i];
         int c = book_partid(prm.book, nid);
-        if (c != prm.book.rank && prm.cache_map != nullptr && __ldg(prm.cache_map + nid) >= 0) c = P;
-        prm.cls[i] = (uint8_t)c;
+        int32_t d = c;
+        // the ONE cache probe of this node: the scatter below and the fused gather read `desc`
+        if (!book_is_local(prm.book, c) && prm.cache.nodes > 0) {
+          const int32_t row = cache_lookup(prm.cache, nid, pol);
+          if (row >= 0) {
+            c = P;
+            d = ~row;
+          }
+        }
+        prm.desc[i] = d;
         atomicAdd(&s_hist[c], 1u);
       }
     }
@@ -182,7 +259,8 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_scatter(const __grid_co
       __syncthreads();
       const int64_t i = base + r * kSplitThreads + threadIdx.x;
       const bool valid = i < n;
-      const int c = valid ? (int)prm.cls[i] : (kClasses + lane);  // invalid lanes never match each other
+      const int32_t d = valid ? prm.desc[i] : 0;
+      const int c = valid ? (d < 0 ? P : (int)d) : (kClasses + lane);  // invalid lanes never match each other
       const uint32_t peers = __match_any_sync(kFullMask, c);
       const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
       if (valid && rank_in_warp == 0) s_warpcnt[warp][c] = __popc(peers);
@@ -190,8 +268,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_scatter(const __grid_co
       if (valid) {
         uint32_t pos = s_run[c] + rank_in_warp;
         for (int w = 0; w < warp; ++w) pos += s_warpcnt[w][c];
-        const int64_t nid = (int64_t)ids[i];
-        prm.bucket_ids[pos] = (c == P) ? (int64_t)__ldg(prm.cache_map + nid) : nid;
+        prm.bucket_ids[pos] = (d < 0) ? (int64_t)(~d) : (int64_t)ids[i];
         prm.perm[i] = (int64_t)pos;
       }
       __syncthreads();
@@ -246,35 +323,56 @@ int spp_nid_is_local(const int64_t* offsets, int num_parts, int rank, const int6
   return 0;
 }
 
-int spp_cache_build_map(const int64_t* cached_vertices, int64_t n_cached, int32_t* cache_map, int64_t num_nodes,
-                        void* stream) {
+int64_t spp_cache_index_bytes(int64_t num_nodes, int64_t n_cached) {
   using namespace spp;
-  if (num_nodes < 0 || n_cached < 0 || n_cached > 0x7fffffffll) return fail(SPP_EINVAL, "spp_cache_build_map: bad sizes");
+  if (num_nodes < 0) num_nodes = 0;
+  if (n_cached < 0) n_cached = 0;
+  const int64_t nblocks = cache_index_blocks(num_nodes);
+  return nblocks * 32 + (n_cached + 1) * 4 + (ceil_div(nblocks > 0 ? nblocks : 1, kIdxThreads) + 1) * 4;
+}
+
+int spp_cache_build_index(const int64_t* cached_vertices, int64_t n_cached, int64_t num_nodes, void* index, void* stream) {
+  using namespace spp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (num_nodes < 0 || num_nodes > (1ll << 31) || n_cached < 0 || n_cached > 0x7fffffffll)
+    return fail(SPP_EINVAL, "spp_cache_build_index: bad sizes");
   if (num_nodes == 0) return 0;
-  if (!cache_map || (n_cached > 0 && !cached_vertices)) return fail(SPP_EINVAL, "spp_cache_build_map: null pointer");
-  k_fill_i32<<<ew_grid(num_nodes), kEwThreads, 0, (cudaStream_t)stream>>>(cache_map, num_nodes, -1);
-  SPP_KERNEL_CHECK("k_fill_i32");
-  if (n_cached > 0) {
-    k_cache_scatter<<<ew_grid(n_cached), kEwThreads, 0, (cudaStream_t)stream>>>(cached_vertices, n_cached, cache_map, num_nodes);
-    SPP_KERNEL_CHECK("k_cache_scatter");
-  }
+  if (!index || (n_cached > 0 && !cached_vertices)) return fail(SPP_EINVAL, "spp_cache_build_index: null pointer");
+  const int64_t nblocks = cache_index_blocks(num_nodes);
+  uint32_t* blocks = reinterpret_cast<uint32_t*>(index);
+  int32_t* rank2row = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(index) + nblocks * 32);
+  uint32_t* sums = reinterpret_cast<uint32_t*>(rank2row + n_cached + 1);
+  SPP_CUDA(cudaMemsetAsync(blocks, 0, (size_t)nblocks * 32, st));
+  SPP_CUDA(cudaMemsetAsync(rank2row, 0xFF, (size_t)(n_cached + 1) * 4, st));
+  if (n_cached == 0) return 0;
+  k_cache_setbits<<<ew_grid(n_cached), kEwThreads, 0, st>>>(cached_vertices, n_cached, blocks, num_nodes);
+  SPP_KERNEL_CHECK("k_cache_setbits");
+  const int ctas = (int)ceil_div(nblocks, kIdxThreads);
+  k_cache_block_counts<<<ctas, kIdxThreads, 0, st>>>(blocks, nblocks, sums);
+  SPP_KERNEL_CHECK("k_cache_block_counts");
+  k_cache_scan_sums<<<1, 1024, 0, st>>>(sums, ctas);
+  SPP_KERNEL_CHECK("k_cache_scan_sums");
+  k_cache_add_base<<<ctas, kIdxThreads, 0, st>>>(blocks, nblocks, sums);
+  SPP_KERNEL_CHECK("k_cache_add_base");
+  k_cache_rank2row<<<ew_grid(n_cached), kEwThreads, 0, st>>>(cached_vertices, n_cached, make_cache_index(index, num_nodes), rank2row);
+  SPP_KERNEL_CHECK("k_cache_rank2row");
   return 0;
 }
 
-int spp_nid_is_cached(const int32_t* cache_map, const int64_t* nids, int64_t n, uint8_t* out, void* stream) {
+int spp_nid_is_cached(const void* index, int64_t num_nodes, const int64_t* nids, int64_t n, uint8_t* out, void* stream) {
   using namespace spp;
   if (n <= 0) return 0;
-  if (!cache_map || !nids || !out) return fail(SPP_EINVAL, "spp_nid_is_cached: null pointer");
-  k_nid_is_cached<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(cache_map, nids, n, out);
+  if (!index || !nids || !out) return fail(SPP_EINVAL, "spp_nid_is_cached: null pointer");
+  k_nid_is_cached<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(make_cache_index(index, num_nodes), nids, n, out);
   SPP_KERNEL_CHECK("k_nid_is_cached");
   return 0;
 }
 
-int spp_nid2cachenid(const int32_t* cache_map, const int64_t* nids, int64_t n, int64_t* out, void* stream) {
+int spp_nid2cachenid(const void* index, int64_t num_nodes, const int64_t* nids, int64_t n, int64_t* out, void* stream) {
   using namespace spp;
   if (n <= 0) return 0;
-  if (!cache_map || !nids || !out) return fail(SPP_EINVAL, "spp_nid2cachenid: null pointer");
-  k_nid2cachenid<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(cache_map, nids, n, out);
+  if (!index || !nids || !out) return fail(SPP_EINVAL, "spp_nid2cachenid: null pointer");
+  k_nid2cachenid<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(make_cache_index(index, num_nodes), nids, n, out);
   SPP_KERNEL_CHECK("k_nid2cachenid");
   return 0;
 }
@@ -283,7 +381,7 @@ int64_t spp_split_scratch_words(int64_t n_max) {
   using namespace spp;
   if (n_max < 0) n_max = 0;
   const int64_t tiles = ceil_div(n_max > 0 ? n_max : 1, kSplitTile);
-  return tiles * kClasses + (kClasses + 15) + ceil_div(n_max, 4) + 4;
+  return n_max + tiles * kClasses + (kClasses + 15) + 4;  // [desc n_max][tile_hist][class_start]
 }
 
 int spp_split_by_owner(const spp_feature_map* m, int use_cache, const void* n_id, int idx_is_64, int64_t n_max,
@@ -296,21 +394,22 @@ int spp_split_by_owner(const spp_feature_map* m, int use_cache, const void* n_id
   if (int r = fill_book(prm.book, m->offsets, m->num_parts, m->rank, "spp_split_by_owner")) return r;
   if (m->rank < 0 || m->rank >= m->num_parts) return fail(SPP_EINVAL, "spp_split_by_owner: rank %d out of range", m->rank);
   if (!bucket_counts || !scratch) return fail(SPP_EINVAL, "spp_split_by_owner: null pointer");
-  if (use_cache && !m->cache_map) return fail(SPP_EINVAL, "spp_split_by_owner: use_cache without a cache_map");
+  if (use_cache && !m->cache_index) return fail(SPP_EINVAL, "spp_split_by_owner: use_cache without a cache index");
+  if (m->local_parts) prm.book.local_mask = m->local_parts | (1u << m->rank);
   if (n_max < 0) return fail(SPP_EINVAL, "spp_split_by_owner: negative n_max");
   if (n_max > 0 && (!n_id || !bucket_ids || !perm)) return fail(SPP_EINVAL, "spp_split_by_owner: null pointer");
   if (n_max >= (1ll << 32)) return fail(SPP_EUNSUPPORTED, "spp_split_by_owner: n_max too large");
   prm.n_id = n_id;
   prm.n_dev = n_dev;
   prm.n_max = n_max;
-  prm.cache_map = use_cache ? m->cache_map : nullptr;
+  prm.cache = make_cache_index(use_cache ? m->cache_index : nullptr, m->cache_index_nodes);
   prm.bucket_ids = bucket_ids;
   prm.perm = perm;
   prm.bucket_counts = bucket_counts;
   prm.tiles_max = ceil_div(n_max > 0 ? n_max : 1, kSplitTile);
-  prm.tile_hist = reinterpret_cast<uint32_t*>(scratch);
+  prm.desc = scratch;
+  prm.tile_hist = reinterpret_cast<uint32_t*>(scratch + n_max);
   prm.class_start = prm.tile_hist + prm.tiles_max * kClasses;
-  prm.cls = reinterpret_cast<uint8_t*>(prm.class_start + kClasses + 15);
   const int64_t cap = (int64_t)num_sms() * 8;
   const int grid = (int)(prm.tiles_max < cap ? prm.tiles_max : cap);
   if (idx_is_64) k_split_hist<int64_t><<<grid, kSplitThreads, 0, st>>>(prm);

@@ -59,8 +59,11 @@ extern "C" int spp_batch_enqueue(const spp_batch_job* j) {
       return r;
     trace_mark(kTrGather, 0, gst);
   } else if (j->feature_mode == 2) {
-    if (int r = spp_gather_partitioned(&j->fmap, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->x_out,
-                                       j->ws.max_nodes, nullptr, gst))
+    // the owner split (when it ran) left one source descriptor per node in its scratch: the gather
+    // reads them sequentially instead of probing the cache index a second time
+    if (int r = spp_gather_partitioned(&j->fmap, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev,
+                                       j->do_split ? j->split_scratch : nullptr, j->x_out, j->ws.max_nodes,
+                                       j->gather_counters, gst))
       return r;
     trace_mark(kTrGather, 0, gst);
   }

@@ -469,23 +469,28 @@ class Cache:
         self._cached_features = (cached_features if cached_features is not None
                                  else torch.empty((0, 0), dtype=torch.float16))
         self._map: Optional[torch.Tensor] = None
+        self._map_nodes = 0
 
     rank = property(lambda self: self._rank)
     world_size = property(lambda self: self._world_size)
     cached_vertices = property(lambda self: self._cached_vertices)
     cached_features = property(lambda self: self._cached_features)
 
-    def device_map(self, num_nodes: int) -> torch.Tensor:
-        if self._map is None or self._map.numel() < num_nodes:
+    def device_index(self, num_nodes: int):
+        """``(index, nodes)``: the L2-resident lookup structure over node ids ``[0, nodes)``
+        (``spp_cache_build_index``: membership bits + rank -> cache row), built on first use."""
+        if self._map is None or self._map_nodes < num_nodes:
             device = _device()
             cv = self._cached_vertices.to(device=device, dtype=torch.int64).contiguous()
             if cv.numel() > 0:
                 num_nodes = max(num_nodes, int(cv.max().item()) + 1)
-            m = torch.empty(max(num_nodes, 1), dtype=torch.int32, device=device)
-            check(_lib.load().spp_cache_build_map(cv.data_ptr(), cv.numel(), m.data_ptr(), m.numel(), _stream_ptr()),
-                  "spp_cache_build_map")
-            self._map = m
-        return self._map
+            num_nodes = max(int(num_nodes), 1)
+            L = _lib.load()
+            m = torch.empty(int(L.spp_cache_index_bytes(num_nodes, cv.numel())), dtype=torch.uint8, device=device)
+            check(L.spp_cache_build_index(cv.data_ptr(), cv.numel(), num_nodes, m.data_ptr(), _stream_ptr()),
+                  "spp_cache_build_index")
+            self._map, self._map_nodes = m, num_nodes
+        return self._map, self._map_nodes
 
     def device_features(self) -> torch.Tensor:
         return _resident(self._cached_features, None, "cache_features")
@@ -498,10 +503,9 @@ class Cache:
     def _lookup(self, nids: torch.Tensor, fn, dtype):
         device = _device()
         ids = nids.to(device=device, dtype=torch.int64).contiguous()
-        need = int(ids.max().item()) + 1 if ids.numel() else 1
-        m = self.device_map(need)
+        m, nodes = self.device_index(1)  # ids beyond the index are "not cached"
         out = torch.empty(ids.shape, dtype=dtype, device=device)
-        check(fn(m.data_ptr(), ids.data_ptr(), ids.numel(), out.data_ptr(), _stream_ptr()), "cache lookup")
+        check(fn(m.data_ptr(), nodes, ids.data_ptr(), ids.numel(), out.data_ptr(), _stream_ptr()), "cache lookup")
         return out if nids.is_cuda else out.cpu()
 
     def nid_is_cached(self, nids: torch.Tensor) -> torch.Tensor:
@@ -512,11 +516,13 @@ class Cache:
 
 
 def make_feature_map(offsets: Sequence[int], rank: int, tables: Sequence[Optional[torch.Tensor]],
-                     cache_table: Optional[torch.Tensor] = None, cache_map: Optional[torch.Tensor] = None,
+                     cache_table: Optional[torch.Tensor] = None, cache_index=None,
                      table_ptrs: Optional[Sequence[int]] = None, table_pitch: int = 0,
-                     cache_pitch: int = 0) -> FeatureMap:
+                     cache_pitch: int = 0, local_parts: Sequence[int] = ()) -> FeatureMap:
     """Fill the C ``spp_feature_map``: ``tables[p]`` are device tensors (local partitions) and/or
-    ``table_ptrs[p]`` raw device pointers of IPC-mapped peer partitions."""
+    ``table_ptrs[p]`` raw device pointers of IPC-mapped peer partitions; ``cache_index`` is
+    ``Cache.device_index(num_nodes)``; ``local_parts`` lists further partitions resident on this
+    GPU (fewer GPUs than partitions)."""
     P = len(offsets) - 1
     fm = FeatureMap()
     fm.num_parts = P
@@ -531,9 +537,16 @@ def make_feature_map(offsets: Sequence[int], rank: int, tables: Sequence[Optiona
             ptr = tables[p].data_ptr()
         fm.tables[p] = ptr
     fm.cache_table = cache_table.data_ptr() if cache_table is not None and cache_table.numel() > 0 else None
-    fm.cache_map = cache_map.data_ptr() if (cache_map is not None and fm.cache_table) else None
+    if cache_index is not None and fm.cache_table:
+        fm.cache_index, fm.cache_index_nodes = cache_index[0].data_ptr(), int(cache_index[1])
+    else:
+        fm.cache_index, fm.cache_index_nodes = None, 0
     fm.table_pitch = int(table_pitch)
     fm.cache_pitch = int(cache_pitch)
+    mask = 0
+    for p in local_parts:
+        mask |= 1 << int(p)
+    fm.local_parts = mask
     return fm
 
 
@@ -569,6 +582,7 @@ class Config:
         self.partition_tables = None
         self.peer_table_ptrs = None
         self.peer_table_pitch = 0
+        self.local_parts = None  # further partitions resident on this GPU (fewer GPUs than partitions)
         self.fused_gather = True
 
 
@@ -788,6 +802,8 @@ class Session:
         self.remote_frequency_tensor = torch.empty(0, dtype=torch.int64)
         self.remote_vertices_ordered_by_freq = torch.empty(0, dtype=torch.int64)
         self._slice_result = None
+        self._slice_pending = None
+        self._slice_stream = None
         # the side streams must see set-up work (uploads, cache map) issued on the current stream
         cur = torch.cuda.current_stream()
         for s in self._slots:
@@ -860,12 +876,14 @@ class Session:
         # an empty cache makes the cache branch (fast_sampler.cpp:1108-1260) produce exactly what the
         # no-cache branch (:1031-1107) produces, so it takes the kernel path without a cache map
         self._use_cache = bool(cfg.use_cache) and cfg.cache.cached_vertices.numel() > 0
-        self._cache_map = cfg.cache.device_map(self._g.num_nodes) if self._use_cache else None
+        self._cache_map = cfg.cache.device_index(self._g.num_nodes) if self._use_cache else None
         self._cache_feats = cfg.cache.device_features() if self._use_cache else None
         # book-only map for the split kernel
-        self._split_fm = make_feature_map(off, self._rank, [None] * self._P)
+        local_parts = [int(p) for p in (getattr(cfg, "local_parts", None) or ())]
+        self._split_fm = make_feature_map(off, self._rank, [None] * self._P, local_parts=local_parts)
         if self._use_cache:
-            self._split_fm.cache_map = self._cache_map.data_ptr()
+            self._split_fm.cache_index = self._cache_map[0].data_ptr()
+            self._split_fm.cache_index_nodes = self._cache_map[1]
         # full map (tables of every partition) for the fused gather, when reachable.  The tables
         # are _FeatureTable objects: every rank derives the same row pitch from (F, dtype).
         if cfg.fused_gather and local is not None:
@@ -898,7 +916,8 @@ class Session:
                 self._part_tables = (tables, ltab)  # keep alive
                 ctab = cfg.cache.device_table() if self._use_cache else None
                 self._fm = make_feature_map(off, self._rank, tables, ctab.storage if ctab else None,
-                                            self._cache_map, ptrs, ltab.pitch, ctab.pitch if ctab else 0)
+                                            self._cache_map, ptrs, ltab.pitch, ctab.pitch if ctab else 0,
+                                            local_parts=local_parts)
 
     def _layout(self, edges0: Optional[int]):
         """(per-hop (rowptr, col) offsets, n_id offset, y offset, total words, node bound) of one
@@ -1029,7 +1048,8 @@ class Session:
                         x = torch.empty((nb, fdim), dtype=fdtype, device=self._device)
                         if nb:
                             check(self._lib.spp_gather_partitioned(ctypes.byref(self._fm), self._row_bytes,
-                                                                   ws.n_ids.data_ptr(), 0, nb, None, x.data_ptr(), nb,
+                                                                   ws.n_ids.data_ptr(), 0, nb, None,
+                                                                   slot.split_scratch.data_ptr(), x.data_ptr(), nb,
                                                                    None, sp), "spp_gather_partitioned")
                         job["x"] = x
                     slot.meta_host[SPP_META_WORDS:].copy_(slot.counts, non_blocking=True)
@@ -1285,22 +1305,39 @@ class Session:
     # -- async_slice_tensors (fast_sampler.cpp:720-775): serve other ranks' requests for rows that
     #    the reference keeps on the host; here those rows are in HBM too -----------------------
     def async_slice_tensors(self, ids: List[torch.Tensor], my_rank: int):
+        """For every requesting rank i: positions of the requested local ids that are host rows in
+        the reference (id >= 0, already offset by the GPU cutoff, fast_trainer/transferers.py:545)
+        and of those that are GPU rows (id < 0), plus the host rows themselves (not for
+        ``my_rank``).  Issued on a side stream; ``wait_slice_tensors`` joins it."""
+        if self._slice_stream is None:
+            self._slice_stream = torch.cuda.Stream(self._device)
+            self._slice_event = torch.cuda.Event()
+        st = self._slice_stream
+        st.wait_stream(torch.cuda.current_stream(self._device))
         res = []
-        for i, t in enumerate(ids):
-            t = t.to(self._device)
-            cpu_pos = torch.nonzero(t >= 0).view(-1)
-            gpu_pos = torch.nonzero(t < 0).view(-1)
-            if i != my_rank and self._x_cpu_dev is not None:
-                x_s = serial_index(self._x_cpu_dev, t[cpu_pos])
-            elif i != my_rank:
-                fdim, fdtype = self._feat_shape
-                x_s = torch.empty((0, fdim), dtype=fdtype, device=self._device)
-            else:
-                x_s = torch.empty(0, dtype=torch.int64, device=self._device)
-            res.append([x_s, cpu_pos, gpu_pos])
-        self._slice_result = res
+        with torch.cuda.stream(st):
+            for i, t in enumerate(ids):
+                t = t.to(self._device, non_blocking=True)
+                host = t >= 0
+                cpu_pos = torch.nonzero(host).view(-1)
+                gpu_pos = torch.nonzero(~host).view(-1)
+                if i != my_rank and self._x_cpu_dev is not None:
+                    x_s = serial_index(self._x_cpu_dev, t[cpu_pos])
+                elif i != my_rank:
+                    fdim, fdtype = self._feat_shape
+                    x_s = torch.empty((0, fdim), dtype=fdtype, device=self._device)
+                else:
+                    x_s = torch.empty(0, dtype=torch.int64, device=self._device)
+                res.append([x_s, cpu_pos, gpu_pos])
+            self._slice_event.record(st)
+        self._slice_pending = res
 
     def wait_slice_tensors(self):
+        if self._slice_pending is None:
+            return None
+        self._slice_event.synchronize()
+        torch.cuda.current_stream(self._device).wait_stream(self._slice_stream)
+        self._slice_result, self._slice_pending = self._slice_pending, None
         return None
 
     def get_slice_tensors(self):

@@ -67,6 +67,7 @@ class MiniBatchPipeline:
                 s.bucket_ids = torch.empty(s.ws.max_nodes, dtype=torch.int64, device=self.device)
                 s.perm = torch.empty(s.ws.max_nodes, dtype=torch.int64, device=self.device)
                 s.counts = torch.zeros(SPP_MAX_PARTS + 2, dtype=torch.int64, device=self.device)
+            s.counters = torch.zeros(3, dtype=torch.int64, device=self.device)  # local / cache / peer rows
             s.meta_host = torch.empty(SPP_META_WORDS, dtype=torch.int64).pin_memory()
             s.job = self._make_job(s)
             self.slots.append(s)
@@ -109,11 +110,13 @@ class MiniBatchPipeline:
                                             ctypes.c_uint64(rng_seed), ctypes.byref(s.ws.c), s.rp, s.cp, self.caps,
                                             None, s.stream.cuda_stream), "spp_sample_minibatch")
 
-    def gather(self, s: _PipeSlot):
+    def gather(self, s: _PipeSlot, count_rows: bool = False):
         n_dev = s.ws.meta_ptr(self.L)
         if self.fm is not None:
             check(self.lib.spp_gather_partitioned(ctypes.byref(self.fm), self.row_bytes, s.ws.n_ids.data_ptr(), 0,
-                                                  s.ws.max_nodes, n_dev, s.x.data_ptr(), s.ws.max_nodes, None,
+                                                  s.ws.max_nodes, n_dev, s.scratch.data_ptr() if self.split else None,
+                                                  s.x.data_ptr(), s.ws.max_nodes,
+                                                  s.counters.data_ptr() if count_rows else None,
                                                   s.stream.cuda_stream), "spp_gather_partitioned")
         elif self.x_table is not None:
             check(self.lib.spp_gather_rows_pitched(self.x_table.ptr, self.x_table.pitch, self.row_bytes,
@@ -133,9 +136,11 @@ class MiniBatchPipeline:
                                               s.perm.data_ptr(), s.counts.data_ptr(), s.scratch.data_ptr(),
                                               s.stream.cuda_stream), "spp_split_by_owner")
 
-    def launch(self, slot: int, seeds_ptr: int, bs: int, rng_seed: int, time_gather: bool = False):
+    def launch(self, slot: int, seeds_ptr: int, bs: int, rng_seed: int, time_gather: bool = False,
+               count_rows: bool = False):
         """One mini-batch on slot ``slot``; returns the (start, end) events around the feature
-        gather when ``time_gather``."""
+        gather when ``time_gather`` (``count_rows``: add the rows served local / cache / peer to
+        the slot's ``counters``)."""
         s = self.slots[slot]
         if not time_gather:  # one C call, exactly what the Session's executor issues
             j = s.job
@@ -146,7 +151,7 @@ class MiniBatchPipeline:
         self.owner_split(s)
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record(s.stream)
-        self.gather(s)
+        self.gather(s, count_rows)
         ev[1].record(s.stream)
         self.labels(s, seeds_ptr, bs)
         return ev

@@ -176,6 +176,7 @@ class FastSamplerConfig:
     partition_tables: Optional[list] = None
     peer_table_ptrs: Optional[list] = None
     peer_table_pitch: int = 0
+    local_parts: Optional[list] = None
     fused_gather: bool = True
 
     def to_fast_sampler(self) -> fast_sampler.Config:

@@ -98,6 +98,50 @@ def features(num_nodes: int, dim: int, dtype=torch.float16, *, seed: int = 2, de
     return out
 
 
+def _id_pattern(ids: torch.Tensor, dim: int, dtype: torch.dtype) -> torch.Tensor:
+    """Bit pattern of feature element (id, j) as a pure function of the GLOBAL vertex id:
+    32-bit wrap-around integer hash, masked so that the pattern is a finite positive number
+    (fp16/bf16: < 2, fp32: < 2).  int16 / int32 tensor [len(ids), dim]."""
+    es = torch.empty(0, dtype=dtype).element_size()
+    if es not in (2, 4):
+        raise ValueError("features_by_id supports 2- and 4-byte element types")
+    i = ids.to(torch.int32).view(-1, 1)
+    j = torch.arange(dim, device=ids.device, dtype=torch.int32).view(1, -1)
+    v = i * 1103515245 + j * 40503 + 12345          # wraps in int32 (two's complement) on every backend
+    v = v ^ (v >> 13)
+    v = v * 1664525 + 1013904223
+    v = v ^ (v >> 11)
+    if es == 2:
+        return (v & 0x3BFF).to(torch.int16)
+    return v & 0x3F7FFFFF
+
+
+def features_by_id(lo: int, hi: int, dim: int, dtype=torch.float16, *, device="cpu",
+                   chunk_rows: int = 1 << 21) -> torch.Tensor:
+    """Rows ``[lo, hi)`` of the synthetic feature matrix whose element (i, j) is a pure function of
+    the global vertex id i -- any rank can regenerate the rows of any vertex, so a gathered batch
+    can be verified (``x == expected_features(n_id)``) without holding the other partitions."""
+    dev = torch.device(device)
+    out = torch.empty((hi - lo, dim), dtype=dtype, device=dev)
+    it = torch.int16 if out.element_size() == 2 else torch.int32
+    ov = out.view(it)
+    for s in range(lo, hi, chunk_rows):
+        e = min(hi, s + chunk_rows)
+        ov[s - lo:e - lo] = _id_pattern(torch.arange(s, e, device=dev), dim, dtype)
+    return out
+
+
+def expected_features(ids: torch.Tensor, dim: int, dtype=torch.float16) -> torch.Tensor:
+    """``features_by_id`` evaluated at arbitrary vertex ids (same device as ``ids``)."""
+    pat = _id_pattern(ids, dim, dtype)
+    return pat.view(dtype)
+
+
+def labels_by_id(ids: torch.Tensor, num_classes: int = 47) -> torch.Tensor:
+    """int64 [n, 1] labels as a pure function of the vertex id."""
+    return ((ids.to(torch.int64) * 2654435761 + 12345) % 1000003 % num_classes).view(-1, 1)
+
+
 def labels(num_nodes: int, num_classes: int = 47, *, seed: int = 3, device="cpu") -> torch.Tensor:
     g = torch.Generator(device=torch.device(device))
     g.manual_seed(seed)

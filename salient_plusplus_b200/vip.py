@@ -47,13 +47,16 @@ def vip_probabilities(rowptr: torch.Tensor, col: torch.Tensor, train_idx: torch.
     return 1.0 - not_total                                     # ddp.py:229-233
 
 
-def select_cache_vertices(vip: torch.Tensor, partition_offsets: torch.Tensor, rank: int, num_to_cache: int) -> torch.Tensor:
-    """Global ids to replicate on ``rank``: owner-major, VIP-descending inside each owner."""
+def select_cache_vertices(vip: torch.Tensor, partition_offsets: torch.Tensor, rank: int, num_to_cache: int,
+                          local_parts: Sequence[int] = ()) -> torch.Tensor:
+    """Global ids to replicate on ``rank``: owner-major, VIP-descending inside each owner.
+    ``local_parts``: further partitions resident on the same GPU (never cached either)."""
     dev = vip.device
     off = partition_offsets.to(dev)
     n = vip.numel()
     score = vip.clone()
-    score[int(off[rank]):int(off[rank + 1])] = 0.0            # local vertices are never cached (ddp.py:433-434,512)
+    for p in sorted(set([int(rank)] + [int(q) for q in local_parts])):
+        score[int(off[p]):int(off[p + 1])] = 0.0              # local vertices are never cached (ddp.py:433-434,512)
     k = min(int(num_to_cache), int(torch.count_nonzero(score).item()))   # ddp.py:436-437
     if k <= 0:
         return torch.empty(0, dtype=torch.int64, device=dev)
@@ -67,7 +70,8 @@ def select_cache_vertices(vip: torch.Tensor, partition_offsets: torch.Tensor, ra
 def create_vip_cache(rowptr: torch.Tensor, col: torch.Tensor, train_idx_local: torch.Tensor, batch_size: int,
                      fanouts: Sequence[int], partition_offsets: torch.Tensor, rank: int, cache_pct: float,
                      local_features: torch.Tensor, partition_tables: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                     peer_table_ptrs: Optional[Sequence[int]] = None, vip: Optional[torch.Tensor] = None) -> Cache:
+                     peer_table_ptrs: Optional[Sequence[int]] = None, vip: Optional[torch.Tensor] = None,
+                     local_parts: Sequence[int] = ()) -> Cache:
     """Builds the replicated cache of ``rank``.  The feature rows come straight out of the owners'
     partitions (local tensors in ``partition_tables`` and/or IPC-mapped ``peer_table_ptrs``; with a
     process group of matching size they are exchanged automatically)."""
@@ -78,7 +82,7 @@ def create_vip_cache(rowptr: torch.Tensor, col: torch.Tensor, train_idx_local: t
         vip = vip_probabilities(rowptr, col, train_idx_local, batch_size, fanouts)
     # `vip` may be any per-vertex score (e.g. degrees for cache_strategy == "degree", ddp.py:487-495)
     num = int(n / P * (cache_pct / 100.0))                     # ddp.py:421
-    cv = select_cache_vertices(vip, partition_offsets, rank, num)
+    cv = select_cache_vertices(vip, partition_offsets, rank, num, local_parts)
     ltab = feature_table(local_features)
     tables = [None] * P
     ptrs = [0] * P
@@ -98,10 +102,10 @@ def create_vip_cache(rowptr: torch.Tensor, col: torch.Tensor, train_idx_local: t
             raise _lib.SalientB200Error("create_vip_cache: peer partitions are not reachable")
         ptrs = got
         ptrs[rank] = 0
-    fm = make_feature_map(off, rank, tables, None, None, ptrs, ltab.pitch, 0)
+    fm = make_feature_map(off, rank, tables, None, None, ptrs, ltab.pitch, 0, local_parts=local_parts)
     feats = torch.empty((cv.numel(), ltab.dim), dtype=ltab.dtype, device=dev)
     if cv.numel():
         check(_lib.load().spp_gather_partitioned(ctypes.byref(fm), ltab.row_bytes, cv.data_ptr(), 1, cv.numel(), None,
-                                                 feats.data_ptr(), cv.numel(), None, _stream_ptr()),
+                                                 None, feats.data_ptr(), cv.numel(), None, _stream_ptr()),
               "spp_gather_partitioned")
     return Cache(rank, P, cv, feats)

@@ -30,12 +30,12 @@ def test_exports_match_header(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.EXPORTED) == names
-    assert lib.spp_abi_version() == 1
+    assert lib.spp_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     from salient_plusplus_b200 import _lib
-    assert ctypes.sizeof(_lib.FeatureMap) == 4 + 4 + 17 * 8 + 16 * 8 + 8 + 8 + 16
+    assert ctypes.sizeof(_lib.FeatureMap) == 4 + 4 + 17 * 8 + 16 * 8 + 8 + 8 + 8 + 16 + 8
     assert ctypes.sizeof(_lib.Graph) == 32
     assert ctypes.sizeof(_lib.SamplerWs) == 104
     assert ctypes.sizeof(_lib.SamplerSizes) == 6 * 8 + 2 * 8 * 8
@@ -64,7 +64,11 @@ def test_sampler_sizes_host_only(lib):
     assert lib.spp_sampler_sizes(8, full, 1, 0, 100, 9, ctypes.byref(out)) == 0 and out.hop_edges[0] == 72
     assert lib.spp_sampler_sizes(8, sizes, 99, 0, 0, 0, ctypes.byref(out)) != 0
     assert b"n_hops" in lib.spp_last_error()
-    assert lib.spp_split_scratch_words(0) > 0 and lib.spp_split_scratch_words(10 ** 6) > 10 ** 6 // 4
+    assert lib.spp_split_scratch_words(0) > 0 and lib.spp_split_scratch_words(10 ** 6) > 10 ** 6
+    # cache index: one 32-byte block per 224 ids + 4 bytes per cached vertex (+ scan scratch): ~N/7 bytes
+    b = lib.spp_cache_index_bytes(111059956, 2082374)
+    assert 111059956 // 7 + 4 * 2082374 <= b <= 111059956 // 7 + 4 * 2082374 + 64 * 1024
+    assert lib.spp_cache_index_bytes(0, 0) > 0
 
 
 def test_argument_errors_do_not_need_a_gpu(lib):
@@ -118,7 +122,8 @@ int main(void) {
   if (s.max_nodes != 1081344) return 3;
   if (spp_gather_rows(0, 0, 0, 1, 1, 0, 0, 1, 0) == 0) return 4;   /* bad row_bytes must fail */
   printf("%s\\n", spp_last_error());
-  return sizeof(spp_batch_job) == 832 ? 0 : 5;
+  printf("sizes %d %d %d\\n", (int)sizeof(spp_batch_job), (int)sizeof(spp_feature_map), (int)sizeof(spp_sampler_ws));
+  return 0;
 }
 ''')
     exe = tmp_path / "abi"
@@ -129,3 +134,6 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "row_bytes" in out.stdout
+    # the ctypes mirrors have exactly the C layout
+    want = "sizes %d %d %d" % (ctypes.sizeof(_lib.BatchJob), ctypes.sizeof(_lib.FeatureMap), ctypes.sizeof(_lib.SamplerWs))
+    assert want in out.stdout, (want, out.stdout)

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.01",
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.002",
                         "--steps", "3", "--warmup", "3"], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
@@ -19,7 +19,20 @@ def test_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["steps"] == 3 and line["warmup"] >= 3
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "batches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["gpu_launches"] == 0 and line["config"]["workload"].startswith("ogbn-products-shaped")
+    assert line["gpu_launches"] == 0 and line["config"]["workload"].startswith("ogbn-papers100M-shaped")
+
+
+def test_reference_arm_distributed_sessions_at_two_gpus():
+    """N > 1: rank 0 drains N distributed reference Sessions (book + cache), cores / N threads each."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--scale",
+                        "0.002", "--steps", "4", "--warmup", "3"], cwd=ROOT, env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference-distributed" and line["config"]["feature_partitions"] == 8
+    assert line["e2e"]["value"] == line["value"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

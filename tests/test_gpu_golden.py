@@ -97,7 +97,7 @@ def test_distributed_binning_equals_reference(fs, samp, dist, tag):
     use_cache = tag == "c"
     cv = t(dist["cached_vertices"])
     cache = fs.Cache(rank, P, cv, torch.zeros(cv.numel(), 4).half())
-    cmap = cache.device_map(int(off[-1]))
+    cmap = cache.device_index(int(off[-1]))
     lidx = dist["lidx"]
     for k in range(int(dist[f"{tag}_num_batches"])):
         p = f"{tag}{k}"
@@ -109,7 +109,7 @@ def test_distributed_binning_equals_reference(fs, samp, dist, tag):
         n = ids_dev.numel()
         fm = make_feature_map(off.tolist(), rank, [None] * P)
         if use_cache:
-            fm.cache_map = cmap.data_ptr()
+            fm.cache_index, fm.cache_index_nodes = cmap[0].data_ptr(), cmap[1]
         scratch = torch.empty(int(L.spp_split_scratch_words(n)), dtype=torch.int32, device="cuda")
         ids = torch.empty(n, dtype=torch.int64, device="cuda")
         perm = torch.empty(n, dtype=torch.int64, device="cuda")

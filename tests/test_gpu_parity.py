@@ -316,7 +316,7 @@ def _split_via_abi(n_id, off, rank, use_cache, cache_map):
     n = n_id.numel()
     fm = make_feature_map(off, rank, [None] * P)
     if use_cache:
-        fm.cache_map = cache_map.data_ptr()
+        fm.cache_index, fm.cache_index_nodes = cache_map[0].data_ptr(), cache_map[1]
     words = int(L.spp_split_scratch_words(n))
     scratch = torch.empty(words, dtype=torch.int32, device="cuda")
     ids = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
@@ -326,6 +326,13 @@ def _split_via_abi(n_id, off, rank, use_cache, cache_map):
                                     n, None, ids.data_ptr(), perm.data_ptr(), counts.data_ptr(), scratch.data_ptr(),
                                     torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
+    # the per-node source descriptors the split leaves for the fused gather: p >= 0 -> partition, < 0 -> ~cache row
+    desc = scratch[:n].cpu().numpy()
+    pos = perm[:n].cpu().numpy()
+    bounds = np.cumsum([0] + counts.cpu().numpy()[:P + 1].tolist())
+    owner = np.searchsorted(bounds, pos, side="right") - 1
+    assert np.array_equal(np.where(desc < 0, P, desc), owner)
+    assert np.array_equal((~desc)[desc < 0], ids[:n].cpu().numpy()[pos[desc < 0]])
     return ids[:n].cpu().numpy(), perm[:n].cpu().numpy(), counts.cpu().numpy()
 
 
@@ -341,7 +348,7 @@ def test_split_by_owner_bitexact(fs, P, rank, use_cache, idt):
     lo, hi = off[rank], off[rank + 1]
     cv = cv[(cv < lo) | (cv >= hi)]                           # caches hold remote vertices only (ddp.py:512)
     cache = fs.Cache(rank, P, cv, torch.zeros(cv.numel(), 4).half())
-    cmap = cache.device_map(N)
+    cmap = cache.device_index(N)
     ids, perm, counts = _split_via_abi(n_id.to(idt).cuda(), off, rank, use_cache, cmap)
     pn, cn, operm, _ = O.distributed_binning(n_id.numpy(), np.array(off), rank, P, 10 ** 9, use_cache,
                                              O.Cache(cv.numpy(), N) if use_cache else None)
@@ -375,7 +382,7 @@ def test_gather_partitioned_equals_global_gather(fs, P, rank, use_cache, dim, dt
         cv = torch.randperm(N, generator=g)[:4000]
         cv = cv[(cv < off[rank]) | (cv >= off[rank + 1])]
         cache = fs.Cache(rank, P, cv, X[cv].contiguous())
-        cmap, cfeat = cache.device_map(N), cache.device_features()
+        cmap, cfeat = cache.device_index(N), cache.device_features()
         # poison the peer copies of cached rows: they must be served from the cache
         for p in range(P):
             if p != rank:
@@ -386,10 +393,24 @@ def test_gather_partitioned_equals_global_gather(fs, P, rank, use_cache, dim, dt
     counters = torch.zeros(3, dtype=torch.int64, device="cuda")
     ids = n_id.cuda()
     _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), dim * X.element_size(), ids.data_ptr(), 1, ids.numel(), None,
-                                        out.data_ptr(), ids.numel(), counters.data_ptr(),
+                                        None, out.data_ptr(), ids.numel(), counters.data_ptr(),
                                         torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), X[n_id])
+    # same rows through the descriptors of the owner split (what a Session's batch does)
+    words = int(L.spp_split_scratch_words(ids.numel()))
+    scratch = torch.empty(words, dtype=torch.int32, device="cuda")
+    b_ids, b_perm = torch.empty_like(ids), torch.empty_like(ids)
+    b_counts = torch.zeros(P + 2, dtype=torch.int64, device="cuda")
+    sp = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.spp_split_by_owner(ctypes.byref(fm), int(use_cache), ids.data_ptr(), 1, ids.numel(), None, b_ids.data_ptr(),
+                                    b_perm.data_ptr(), b_counts.data_ptr(), scratch.data_ptr(), sp))
+    out2 = torch.zeros_like(out)
+    counters2 = torch.zeros(3, dtype=torch.int64, device="cuda")
+    _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), dim * X.element_size(), ids.data_ptr(), 1, ids.numel(), None,
+                                        scratch.data_ptr(), out2.data_ptr(), ids.numel(), counters2.data_ptr(), sp))
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out) and counters2.tolist() == counters.tolist()
     local = ((n_id >= off[rank]) & (n_id < off[rank + 1])).sum().item()
     c = counters.tolist()
     assert c[0] == local and sum(c) == n_id.numel()

@@ -42,7 +42,7 @@ def test_feature_map_marshalling():
     fm = make_feature_map([0, 10, 25, 40], 1, [None, None, None], None, None, [111, 0, 333], 256, 128)
     assert fm.num_parts == 3 and fm.rank == 1 and list(fm.offsets)[:5] == [0, 10, 25, 40, 40]
     assert fm.tables[0] == 111 and fm.tables[1] is None and fm.tables[2] == 333
-    assert fm.cache_table is None and fm.cache_map is None and fm.table_pitch == 256 and fm.cache_pitch == 128
+    assert fm.cache_table is None and fm.cache_index is None and fm.local_parts == 0 and fm.table_pitch == 256 and fm.cache_pitch == 128
     with pytest.raises(RuntimeError):
         RangePartitionBook(0, 1, torch.arange(40))._off()      # more than SPP_MAX_PARTS partitions
 
@@ -67,7 +67,7 @@ def test_adj_and_batches():
 
 
 def test_struct_sizes_stable():
-    assert ctypes.sizeof(_lib.BatchJob) == 832
+    assert ctypes.sizeof(_lib.BatchJob) == 856
 
 
 def test_prepared_batch_keeps_four_fields_and_owner_fast_path():

@@ -46,9 +46,10 @@ def _worker(rank, world, port, ret):
         dist.all_gather_object(counts, len(ranges))
         assert counts == [3] * world and ranges[-1][1] == local.numel()
         # 3. peer-table exchange protocol with the IPC calls recorded
-        exported, imported = [], []
+        exported, imported, closed = [], [], []
         peer.export_handle = lambda t: (exported.append(t.data_ptr()) or bytes([rank]) * 64, 4096 * rank)
         peer.import_handle = lambda h, o: (imported.append((h[0], o)) or 1_000_000 * (h[0] + 1) + o)
+        peer.close_handle = lambda p_, o: closed.append((p_, o))
         torch.cuda.synchronize = lambda *a, **k: None
         torch.cuda.current_device = lambda: 0
         table = torch.zeros(8, 4)
@@ -58,9 +59,29 @@ def _worker(rank, world, port, ret):
             if p != rank:
                 assert ptrs[p] == 1_000_000 * (p + 1) + 4096 * p
         assert exported == [table.data_ptr()] and sorted(i[0] for i in imported) == [p for p in range(world) if p != rank]
-        # cached on the second call (no new export), and refused when the group size mismatches
-        assert peer.exchange_partition_tables(table, rank, world) == ptrs and len(exported) == 1
+        # second call: every rank takes part in the collective again (no rank may skip it), the
+        # unchanged peer tables are NOT mapped a second time; refused when the group size mismatches
+        assert peer.exchange_partition_tables(table, rank, world) == ptrs and len(imported) == world - 1 and not closed
         assert peer.exchange_partition_tables(table, rank, world + 1) is None
+        # a peer re-exports a table that moved: the stale mapping is closed and replaced
+        if rank == 0:
+            peer.export_handle = lambda t: (bytes([rank]) * 64, 8192)
+        ptrs2 = peer.exchange_partition_tables(table, rank, world)
+        if rank == 1:
+            assert ptrs2[0] == 1_000_000 + 8192 and closed == [(ptrs[0], 0)] and len(imported) == world
+        else:
+            assert ptrs2 == ptrs
+        # a peer that cannot be mapped (other host): every rank agrees on None and the mappings opened
+        # in the failed round are closed again -> the caller falls back to the all_to_all path
+        import socket
+        if rank == 1:
+            socket.gethostname = lambda: "some-other-host"
+        n_closed = len(closed)
+        peer._IMPORTED.clear()
+        assert peer.exchange_partition_tables(table, rank, world) is None
+        assert not peer._IMPORTED and len(closed) >= n_closed
+        assert peer.hosted_partitions(1, 2, 8) == [4, 5, 6, 7]
+        assert peer.partition_pointers([1000, 5000], [0, 10, 20, 30, 40], 2, 4) == [1000, 1040, 5000, 5040]
         ret[rank] = "ok"
     except Exception as e:  # noqa: BLE001
         import traceback

@@ -29,7 +29,7 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    shape, _, bs, desc = B.WORKLOADS[a.workload]
+    shape, _, bs, _, desc = B.WORKLOADS[a.workload]
     n, f, dt, rowptr, col = B.make_graph(shape, a.scale, dev, 0.0, 1)
     x = S.features(n, f, dt, seed=2, device=dev)
     y = S.labels(n, seed=3, device=dev)

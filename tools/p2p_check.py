@@ -108,14 +108,14 @@ for F, dt in ((128, torch.float16), (768, torch.float16)):
         ids = ids.to(torch.int64)
         sp = torch.cuda.current_stream().cuda_stream
         for _ in range(3):
-            _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), rb, ids.data_ptr(), 1, n, None, out.data_ptr(), n, None, sp))
+            _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), rb, ids.data_ptr(), 1, n, None, None, out.data_ptr(), n, None, sp))
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
         e0.record()
         for _ in range(reps):
-            _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), rb, ids.data_ptr(), 1, n, None, out.data_ptr(), n, None, sp))
+            _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), rb, ids.data_ptr(), 1, n, None, None, out.data_ptr(), n, None, sp))
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps

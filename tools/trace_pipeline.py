@@ -30,7 +30,7 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    shape, sizes, bs, desc = B.WORKLOADS[a.workload]
+    shape, sizes, bs, _, desc = B.WORKLOADS[a.workload]
     n, f, dt, rowptr, col = B.make_graph(shape, a.scale, dev, 0.0, 1)
     col = col.to(torch.int32)
     x = S.features(n, f, dt, seed=2, device=dev)
