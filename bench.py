@@ -468,10 +468,18 @@ def ours(args):
     off = S.equal_partition_offsets(n, P)
     offl = [int(v) for v in off.tolist()]
     hosted = peer.hosted_partitions(rank, world, P)       # consecutive partitions resident on this GPU
+    emulate = bool(args.emulate_peers) and world == 1 and P > 1
+    if emulate:
+        # profiling aid (ncu sees one GPU): this GPU plays partition 0 only; the other partitions' tables
+        # also live here but are treated as peers (book search, cache probe, replicated cache) -- every
+        # code path of an N-GPU rank except the NVLink hop
+        hosted = [0]
     prank = hosted[0]                                      # the partition this rank acts as in the book
     blo, bhi = offl[hosted[0]], offl[hosted[-1] + 1]
     need = (W + K) * bs
     idx = S.seeds(n, min(bhi - blo, need), seed=7 + rank, device=dev, lo=blo, hi=bhi)  # federated: local seeds
+    if emulate:
+        blo, bhi = 0, n                                    # ... but every row is materialised here
     if idx.numel() < need:
         idx = idx.repeat((need + idx.numel() - 1) // idx.numel())[:need]
     idx_host = idx.cpu().pin_memory()
@@ -494,12 +502,15 @@ def ours(args):
                 raise SystemExit("peer feature tables are not reachable (no P2P between the GPUs of this box?)")
         else:
             rank_ptrs = [btab.storage.data_ptr()]
-        part_ptrs = peer.partition_pointers(rank_ptrs, offl, world, pitch)
+        if emulate:
+            part_ptrs = [btab.storage.data_ptr() + offl[p] * pitch for p in range(P)]
+        else:
+            part_ptrs = peer.partition_pointers(rank_ptrs, offl, world, pitch)
         x_rank = x_block[:offl[prank + 1] - blo]
         if args.cache_policy == "vip":
             # the reference's policy (driver/drivers/ddp.py:417-446): analytic vertex-inclusion
             # probabilities of this rank's mini-batches (federated: every local vertex can be a seed)
-            probs = V.vip_probabilities(rowptr, col32, torch.arange(blo, bhi, device=dev), bs, sizes)
+            probs = V.vip_probabilities(rowptr, col32, torch.arange(offl[hosted[0]], offl[hosted[-1] + 1], device=dev), bs, sizes)
         else:  # degree ranking (ddp.py:487-495)
             probs = (rowptr[1:] - rowptr[:-1]).to(torch.float64)
         if str(args.cache_pct).lower() == "auto":
@@ -809,7 +820,7 @@ def ours(args):
                        "features": "element (i, j) = pure function of the global vertex id (synthetic.features_by_id)",
                        "nnz": int(col32.numel()), "mean_nodes_per_batch": round(mean_nodes, 1),
                        "streams_in_flight": D, "scale": args.scale, "feature_partitions": P,
-                       "partitions_per_gpu": len(hosted), "cache_rows": int(cache.cached_vertices.numel()),
+                       "partitions_per_gpu": len(hosted), "emulated_peers": emulate, "cache_rows": int(cache.cached_vertices.numel()),
                        "l2": "inputs larger than L2 (feature table + CSR >> 126 MB, random rows)"},
             "gathered_GBps": round(value * mean_nodes * row_bytes / 1e9, 2),
             "parity": {"ok": parity_ok, "batches_checked_per_rank": int(okt[1].item()),
@@ -1062,6 +1073,9 @@ def main():
                          "Chung-Lu graph, the worst case for range-partitioned features)")
     ap.add_argument("--parity-batches", type=int, default=3, help="batches per rank verified outside the timed regions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-peers", action="store_true",
+                    help="one GPU only, profiling aid: act as partition 0 of --parts and treat the other partitions "
+                         "(resident on the same GPU) as peers, with the replicated cache in front of them")
     ap.add_argument("--no-features", action="store_true",
                     help="A/B experiments with --device-only: sampler alone (no feature / label gather)")
     ap.add_argument("--device-only", action="store_true",

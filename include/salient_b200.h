@@ -42,6 +42,11 @@ extern "C" {
 #define SPP_META_OVERFLOW 24        /* !=0: a buffer bound was exceeded on the device           */
 
 int spp_abi_version(void);
+/* run-time tunables (A/B tools, tests); defaults come from the SPP_* environment variables:
+ *   "gather_ctas_per_sm" (0 = automatic), "gather_bulk" (-1 automatic, 0 never, 1 whenever the rows are
+ *   multiples of 16 bytes: bulk-copy flavour of the gather), "bulk_tile" (bytes), "bulk_stages",
+ *   "bulk_ctas_per_sm" */
+int spp_tune(const char* key, int value);
 const char* spp_last_error(void);
 /* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
 uint64_t spp_launch_count(void);

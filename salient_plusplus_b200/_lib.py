@@ -25,7 +25,7 @@ META_EDGES0 = 12
 META_OVERFLOW = 24
 
 EXPORTED = [
-    "spp_abi_version", "spp_last_error", "spp_launch_count",
+    "spp_abi_version", "spp_tune", "spp_last_error", "spp_launch_count",
     "spp_gather_rows", "spp_gather_rows_pitched", "spp_gather_partitioned",
     "spp_nid2partid", "spp_nid2localnid", "spp_nid_is_local",
     "spp_cache_index_bytes", "spp_cache_build_index", "spp_nid_is_cached", "spp_nid2cachenid",
@@ -113,6 +113,7 @@ def load() -> ctypes.CDLL:
     vp, i64, i32, ci = c_void_p, c_int64, c_int32, c_int
     L.spp_abi_version.restype = ci
     L.spp_last_error.restype = c_char_p
+    L.spp_tune.argtypes = [c_char_p, ci]
     L.spp_launch_count.restype = c_uint64
     L.spp_gather_rows.argtypes = [vp, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_rows_pitched.argtypes = [vp, i64, i64, vp, ci, i64, vp, vp, i64, vp]
@@ -189,6 +190,11 @@ def trace_end(cap: int = 4096):
     st, ms = (c_uint64 * cap)(), (ctypes.c_double * cap)()
     n = int(load().spp_trace_end(lab, hop, st, ms, cap))
     return [(TRACE_LABELS[lab[i]], int(hop[i]), int(st[i]), float(ms[i])) for i in range(n)]
+
+
+def tune(key: str, value: int) -> None:
+    """Run-time tunable of the library (see spp_tune in the header)."""
+    check(load().spp_tune(key.encode(), int(value)), "spp_tune")
 
 
 def launch_count() -> int:

@@ -34,6 +34,17 @@ AuxStreams* aux_streams(cudaStream_t main);
 // (SPP_FORK overrides the default)
 int pipeline_flags();
 
+// Tunables (runtime.cu): defaults come from the SPP_* environment variables of the same meaning, read
+// once; spp_tune() changes them at run time (A/B tools, tests).  -1 = "not set".
+struct Tunables {
+  int gather_ctas_per_sm;  // SPP_GATHER_CTAS_PER_SM   0 = automatic
+  int gather_bulk;         // SPP_GATHER_BULK          -1 automatic, 0 never, 1 whenever rows allow it
+  int bulk_tile;           // SPP_BULK_TILE            bytes per tile of the bulk-copy gather
+  int bulk_stages;         // SPP_BULK_STAGES
+  int bulk_ctas_per_sm;    // SPP_BULK_CTAS_PER_SM
+};
+Tunables& tunables();
+
 // true when `p` is a pointer spp_ipc_import returned (a peer GPU's memory mapped into this process)
 bool ipc_imported(const void* p);
 

@@ -191,14 +191,161 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
   }
 }
 
-// 0 = not forced by the environment
-static int gather_ctas_per_sm_env() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SPP_GATHER_CTAS_PER_SM");
-    v = (e && atoi(e) > 0) ? atoi(e) : 0;
+// ================================================================================================
+// Bulk-copy flavour for rows whose size and addresses are multiples of 16 bytes (128-d fp16 papers
+// rows, 768-d MAG rows, fp32 arxiv rows): every row travels global -> shared as ONE asynchronous
+// bulk copy (cp.async.bulk, the 1-D TMA path) and every tile leaves shared -> global as ONE bulk
+// store.  No data passes through registers, a warp keeps kBulkStages - 1 tiles (~8 KB each) in
+// flight with 32 threads, and the requests that reach the fabric are whole rows rather than
+// 16-byte fragments -- which is what the NVLink-bound peer fetch wants.
+// Each warp is an independent pipeline: lane i resolves row i of the tile and issues its copy,
+// lane 0 arms the tile's mbarrier with the byte count and later issues the tile's bulk store.
+// ================================================================================================
+constexpr int kBulkWarps = 4;       // warps (independent pipelines) per CTA
+constexpr int kBulkMaxStages = 8;   // stages per warp: S - 2 tiles being loaded, 2 being stored
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <bool kPartitioned, typename IdxT>
+__global__ void __launch_bounds__(kBulkWarps * 32) k_gather_bulk(const __grid_constant__ GatherParams prm, const int tile_rows,
+                                                                  const int stages) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ uint64_t s_bar[kBulkWarps][kBulkMaxStages];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t n = prm.n_max;
+  if (prm.n_dev != nullptr) {
+    const int64_t nd = *prm.n_dev;
+    n = nd < n ? nd : n;
   }
-  return v;
+  const uint32_t row_bytes = (uint32_t)prm.row_bytes;
+  const uint32_t stage_bytes = (uint32_t)tile_rows * row_bytes;
+  unsigned char* my = s_raw + (size_t)warp * stages * stage_bytes;
+  uint64_t* bar = s_bar[warp];
+  if (lane == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(bar + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const IdxT* __restrict__ idx = reinterpret_cast<const IdxT*>(prm.idx);
+  const int64_t num_tiles = (n + tile_rows - 1) / tile_rows;
+  const int64_t wglobal = (int64_t)blockIdx.x * kBulkWarps + warp;
+  const int64_t wstride = (int64_t)gridDim.x * kBulkWarps;
+  uint64_t pol = 0;
+  if constexpr (kPartitioned) pol = l2_policy_evict_last();
+  unsigned long long cnt0 = 0, cnt1 = 0, cnt2 = 0;
+
+  // the id (and source descriptor) of the tile that is ISSUED next is loaded one step ahead
+  RowResolver<kPartitioned> nxt;
+  auto load_row = [&](int64_t tile, RowResolver<kPartitioned>& r) {
+    r.on = false;
+    if (tile < num_tiles && lane < tile_rows) {
+      const int64_t row = tile * tile_rows + lane;
+      if (row < n) {
+        r.id = (int64_t)idx[row];
+        r.on = true;
+      }
+    }
+  };
+  auto issue = [&](int64_t tile, int stage, RowResolver<kPartitioned>& r) {
+    const int64_t row0 = tile * tile_rows;
+    const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
+    if (lane == 0) mbar_expect_tx(bar + stage, (uint32_t)rows * row_bytes);
+    __syncwarp();
+    r.begin_lookup(prm, row0 + lane, pol);
+    int cls;
+    const char* src = r.finish(prm, cls);
+    if (r.on) bulk_g2s(my + (size_t)stage * stage_bytes + (size_t)lane * row_bytes, src, row_bytes, bar + stage);
+    if constexpr (kPartitioned) {
+      if (prm.counters != nullptr) {
+        const uint32_t m0 = __ballot_sync(kFullMask, cls == 0), m1 = __ballot_sync(kFullMask, cls == 1),
+                       m2 = __ballot_sync(kFullMask, cls == 2);
+        if (lane == 0) {
+          cnt0 += __popc(m0);
+          cnt1 += __popc(m1);
+          cnt2 += __popc(m2);
+        }
+      }
+    }
+  };
+
+  // prologue: stages - 2 tiles in flight
+  int64_t t_issue = wglobal;
+  load_row(t_issue, nxt);
+  int issued = 0;
+  for (; issued < stages - 2 && t_issue < num_tiles; ++issued) {
+    RowResolver<kPartitioned> cur = nxt;
+    load_row(t_issue + wstride, nxt);
+    issue(t_issue, issued, cur);
+    t_issue += wstride;
+  }
+  int k = 0, stage = 0, istage = issued % stages;  // tiles consumed; stage of tile k; stage of the next issue
+  uint32_t parity = 0;
+  for (int64_t tile = wglobal; tile < num_tiles; tile += wstride, ++k) {
+    mbar_wait(bar + stage, parity);
+    if (lane == 0) {
+      const int64_t row0 = tile * tile_rows;
+      const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
+      bulk_s2g(prm.out + row0 * prm.row_bytes, my + (size_t)stage * stage_bytes, (uint32_t)rows * row_bytes);
+      bulk_commit();
+    }
+    if (t_issue < num_tiles) {
+      // the next load goes into the stage of tile k - 2: its store (two commits ago) must have finished reading
+      if (lane == 0) bulk_wait_read<2>();
+      __syncwarp();
+      RowResolver<kPartitioned> cur = nxt;
+      load_row(t_issue + wstride, nxt);
+      issue(t_issue, istage, cur);
+      t_issue += wstride;
+      if (++istage == stages) istage = 0;
+    }
+    if (++stage == stages) {
+      stage = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last stores' reads
+  if constexpr (kPartitioned) {
+    if (prm.counters != nullptr && lane == 0) {
+      if (cnt0) atomicAdd(prm.counters + 0, cnt0);
+      if (cnt1) atomicAdd(prm.counters + 1, cnt1);
+      if (cnt2) atomicAdd(prm.counters + 2, cnt2);
+    }
+  }
 }
 
 // Does any partition table live on another GPU?  Peer tables enter a process through
@@ -208,6 +355,9 @@ static bool map_has_peer_tables(const GatherParams& prm) {
     if (p != prm.book.rank && prm.tables[p] != nullptr && ipc_imported(prm.tables[p])) return true;
   return false;
 }
+
+// decided by the A/B runs under profiles/ (r02_ab_gather_bulk_*.txt)
+static bool bulk_default_for_peers() { return false; }
 
 template <bool kPartitioned>
 static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaStream_t st) {
@@ -224,11 +374,41 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
   // its CTAs 3-5x longer: 2 CTAs / SM keep the link just as busy and leave the sampler kernels of
   // the other in-flight batches three quarters of every SM (+2.6 % at 2 GPUs, +6.6 % at 4 on the
   // products shape, profiles/r01_ab_multi_gather_ctas.txt)
-  int cps = gather_ctas_per_sm_env();
+  const Tunables& tn = tunables();
+  int cps = tn.gather_ctas_per_sm > 0 ? tn.gather_ctas_per_sm : 0;
+  bool peers = false;
+  if constexpr (kPartitioned) peers = map_has_peer_tables(prm);
+  const int bulk_mode = tn.gather_bulk;
+  if (vec_bytes == 16 && prm.row_bytes <= 8192 && (bulk_mode == 1 || (bulk_mode < 0 && peers && bulk_default_for_peers()))) {
+    const int tile_bytes = tn.bulk_tile > 0 ? tn.bulk_tile : 4096;
+    int stages = tn.bulk_stages;
+    if (stages < 3) stages = 3;
+    if (stages > kBulkMaxStages) stages = kBulkMaxStages;
+    const int bcps = tn.bulk_ctas_per_sm > 0 ? tn.bulk_ctas_per_sm : 2;
+    int tile_rows = (int)(tile_bytes / prm.row_bytes);
+    if (tile_rows > 32) tile_rows = 32;
+    if (tile_rows < 1) tile_rows = 1;
+    const size_t smem = (size_t)kBulkWarps * stages * tile_rows * prm.row_bytes;
+    if (smem <= 200 * 1024) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        SPP_CUDA(cudaFuncSetAttribute(k_gather_bulk<kPartitioned, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SPP_CUDA(cudaFuncSetAttribute(k_gather_bulk<kPartitioned, int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+      }
+      const int64_t btiles = ceil_div(prm.n_max, tile_rows);
+      const int64_t bmax = (int64_t)num_sms() * (cps > 0 ? cps : bcps);
+      const int64_t want = ceil_div(btiles, kBulkWarps);
+      const int bgrid = (int)(want < bmax ? want : bmax);
+      if (idx_is_64) k_gather_bulk<kPartitioned, int64_t><<<bgrid, kBulkWarps * 32, smem, st>>>(prm, tile_rows, stages);
+      else k_gather_bulk<kPartitioned, int32_t><<<bgrid, kBulkWarps * 32, smem, st>>>(prm, tile_rows, stages);
+      SPP_KERNEL_CHECK("k_gather_bulk");
+      return 0;
+    }
+  }
   if (cps == 0) {
     cps = 4;
-    if constexpr (kPartitioned)
-      if (map_has_peer_tables(prm)) cps = 2;
+    if (peers) cps = 2;
   }
   const int64_t max_ctas = (int64_t)num_sms() * cps;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);

@@ -87,6 +87,12 @@ static int env_int(const char* name, int dflt) {
   return (e && *e) ? atoi(e) : dflt;
 }
 
+Tunables& tunables() {
+  static Tunables t = {env_int("SPP_GATHER_CTAS_PER_SM", 0), env_int("SPP_GATHER_BULK", -1), env_int("SPP_BULK_TILE", 4096),
+                       env_int("SPP_BULK_STAGES", 6), env_int("SPP_BULK_CTAS_PER_SM", 2)};
+  return t;
+}
+
 int pipeline_flags() {
   static int v = -1;
   if (v < 0) v = env_int("SPP_FORK", 0) & 3;
@@ -151,6 +157,18 @@ int64_t spp_trace_end(int32_t* labels, int32_t* hops, uint64_t* streams, double*
   spp::g_trace.clear();
   cudaGetLastError();
   return n;
+}
+
+int spp_tune(const char* key, int value) {
+  if (!key) return spp::fail(SPP_EINVAL, "spp_tune: null key");
+  spp::Tunables& t = spp::tunables();
+  if (!strcmp(key, "gather_ctas_per_sm")) t.gather_ctas_per_sm = value;
+  else if (!strcmp(key, "gather_bulk")) t.gather_bulk = value;
+  else if (!strcmp(key, "bulk_tile")) t.bulk_tile = value;
+  else if (!strcmp(key, "bulk_stages")) t.bulk_stages = value;
+  else if (!strcmp(key, "bulk_ctas_per_sm")) t.bulk_ctas_per_sm = value;
+  else return spp::fail(SPP_EINVAL, "spp_tune: unknown key '%s'", key);
+  return 0;
 }
 
 int spp_abi_version(void) { return SPP_ABI_VERSION; }

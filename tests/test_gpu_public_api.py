@@ -314,3 +314,59 @@ def test_async_slice_tensors_against_compiled_reference(fs, data):
         if i != rank:
             assert torch.equal(g_[0].cpu(), w_[0]), f"rows of request {i}"
         assert torch.equal(g_[1].cpu(), w_[1]) and torch.equal(g_[2].cpu(), w_[2]), f"positions of request {i}"
+
+
+@pytest.mark.parametrize("dim,dtype", [(128, torch.float16), (768, torch.float16), (128, torch.float32), (8, torch.float16)])
+@pytest.mark.parametrize("tile,stages", [(4096, 6), (8192, 3), (2048, 8), (256, 4)])
+def test_bulk_copy_gather_is_bit_exact(fs, dim, dtype, tile, stages):
+    """The bulk-copy (cp.async.bulk + mbarrier) flavour of the gather, forced on through spp_tune:
+    single table and partitioned (book search + cache index, and through the owner split's source
+    descriptors), ragged row counts, device-side row count."""
+    from salient_plusplus_b200 import _lib
+    from salient_plusplus_b200.fast_sampler import make_feature_map
+    L = _lib.load()
+    N, P, rank = 30000, 4, 1
+    X = S.features_by_id(0, N, dim, dtype, device="cuda")
+    off = S.equal_partition_offsets(N, P).tolist()
+    g = torch.Generator().manual_seed(dim + tile)
+    rb = dim * X.element_size()
+    sp = torch.cuda.current_stream().cuda_stream
+    it = torch.int16 if X.element_size() == 2 else torch.int32
+    try:
+        for k_, v_ in (("gather_bulk", 1), ("bulk_tile", tile), ("bulk_stages", stages)):
+            _lib.tune(k_, v_)
+        launches0 = _lib.launch_count()
+        for n in (1, 31, 33, 4097, 20011):
+            ids = torch.randint(0, N, (n,), generator=g).cuda()
+            out = torch.zeros((n + 3, dim), dtype=dtype, device="cuda")
+            n_dev = torch.tensor([n], dtype=torch.int64, device="cuda")
+            _lib.check(L.spp_gather_rows(X.data_ptr(), rb, ids.data_ptr(), 1, n + 3, n_dev.data_ptr(), out.data_ptr(), n + 3, sp))
+            assert torch.equal(out[:n].view(it), S._id_pattern(ids, dim, dtype)) and not bool(out[n:].any())
+            # partitioned, with a cache holding remote rows
+            cv = torch.randperm(N, generator=g)[:5000]
+            cv = cv[(cv < off[rank]) | (cv >= off[rank + 1])]
+            cache = fs.Cache(rank, P, cv, X[cv.cuda()].contiguous())
+            parts = [X[off[p]:off[p + 1]] for p in range(P)]
+            fm = make_feature_map(off, rank, parts, cache.device_features(), cache.device_index(N))
+            ids32 = ids.to(torch.int32)
+            out.zero_()
+            cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
+            _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), rb, ids32.data_ptr(), 0, n, None, None, out.data_ptr(), n,
+                                                cnt.data_ptr(), sp))
+            assert torch.equal(out[:n].view(it), S._id_pattern(ids, dim, dtype)) and int(cnt.sum()) == n
+            scratch = torch.empty(int(L.spp_split_scratch_words(n)), dtype=torch.int32, device="cuda")
+            b_ids, b_perm = torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, dtype=torch.int64, device="cuda")
+            b_cnt = torch.zeros(P + 2, dtype=torch.int64, device="cuda")
+            _lib.check(L.spp_split_by_owner(ctypes.byref(fm), 1, ids32.data_ptr(), 0, n, None, b_ids.data_ptr(), b_perm.data_ptr(),
+                                            b_cnt.data_ptr(), scratch.data_ptr(), sp))
+            out.zero_()
+            cnt2 = torch.zeros(3, dtype=torch.int64, device="cuda")
+            _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), rb, ids32.data_ptr(), 0, n, None, scratch.data_ptr(),
+                                                out.data_ptr(), n, cnt2.data_ptr(), sp))
+            torch.cuda.synchronize()
+            assert torch.equal(out[:n].view(it), S._id_pattern(ids, dim, dtype)) and cnt2.tolist() == cnt.tolist()
+            assert int(cnt2[1]) == int(b_cnt[P])
+        assert _lib.launch_count() > launches0
+    finally:
+        for k_, v_ in (("gather_bulk", -1), ("bulk_tile", 4096), ("bulk_stages", 6)):
+            _lib.tune(k_, v_)
