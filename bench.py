@@ -327,15 +327,18 @@ def reference_arm(args):
         x = S.features_by_id(0, n, f, dt, device=dev).cpu()
         y = S.labels_by_id(torch.arange(n))
         preroll = 2 * threads
-        need = (preroll + W + K) * bs
+        # a reference "step" is a bundle of m mini-batches so that the K timed steps cover >= 10 waves of
+        # the thread pool (20 single batches on 16-32 threads are ~1 wave: a +-2.7x error)
+        m = max(1, -(-10 * threads // max(K, 1)))
+        need = (preroll + W + K * m) * bs
         if layerwise:
             idx = torch.arange(n, dtype=torch.int64)[:min(n, need)]
         else:
             idx = S.seeds(n, min(n, need), seed=7)
         if idx.numel() < need:
             idx = idx.repeat((need + idx.numel() - 1) // idx.numel())[:need]
-        bps, gbs, timed, kind, _ = run_reference_cpu(rowptr, col, x, y, idx, sizes, bs, threads, W, K, preroll=preroll)
-        sample = (f"{timed} mini-batches after {preroll} pre-roll + {W} warm-up batches (steady state of the thread pool), "
+        bps, gbs, timed, kind, _ = run_reference_cpu(rowptr, col, x, y, idx, sizes, bs, threads, W, K * m, preroll=preroll)
+        sample = (f"{timed} mini-batches ({K} steps of {m}) after {preroll} pre-roll + {W} warm-up batches (steady state of the thread pool), "
                   f"reference fast_sampler.Session with {threads} worker threads (sampling + CPU feature slice, pinned outputs)")
         kind_out = kind
     else:
@@ -351,7 +354,8 @@ def reference_arm(args):
         off = S.equal_partition_offsets(n, P)
         threads_each = max(1, threads // N)
         preroll = 2 * threads_each
-        need = (preroll + W + K + 4) * bs
+        m = max(1, -(-10 * threads_each // max(K, 1)))   # batches per step and Session (>= 10 waves timed)
+        need = (preroll + W + K * m + 4) * bs
         y = S.labels_by_id(torch.arange(n))
         x_blocks, idxs, caches, part_ranks = [], [], [], []
         num_cache = int(n / P * (float(args.cache_pct) / 100.0)) if str(args.cache_pct) != "auto" else int(n / P * 0.15)
@@ -375,10 +379,10 @@ def reference_arm(args):
             caches.append(R.Cache(hosted[0], P, cv, cf))
             part_ranks.append(hosted[0])
         bps, timed = run_reference_distributed(R, rowptr, col, x_blocks, y, idxs, sizes, bs, off, part_ranks, caches,
-                                               threads_each, W, K, preroll)
+                                               threads_each, W, K * m, preroll)
         gbs = None
         kind_out = "reference-distributed"
-        sample = (f"{timed} mini-batches in aggregate after {preroll} pre-roll + {W} warm-up batches per Session; {N} distributed "
+        sample = (f"{timed} mini-batches in aggregate ({K} steps of {m} per Session) after {preroll} pre-roll + {W} warm-up batches per Session; {N} distributed "
                   f"reference Sessions (one per GPU of the run) x {threads_each} worker threads, RangePartitionBook({P} parts) + "
                   f"degree-ranked Cache ({num_cache} rows), gpu_percent 0.999: sampling + owner binning + host-resident row slice")
     line = {
@@ -770,7 +774,7 @@ def ours(args):
     oracle_check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cb = min(K + W, 96)
+        cb = max(96, 10 * threads)   # >= 10 waves of the thread pool, bounded by max_seconds below
         pre = 2 * threads
         rp_h, col_h = rowptr.cpu(), col32.to(torch.int64).cpu()
         x_h = x_block.cpu()
@@ -1000,7 +1004,7 @@ def layerwise(args):
         oracle_check = bool(good)
         parity_ok = parity_ok and oracle_check
         pre = 2 * threads
-        cb = min(K + W, 256)
+        cb = max(256, 10 * threads)
         seeds_c = torch.arange(0, min(n, (cb + pre + 8) * bs), dtype=torch.int64)
         bps, gbs, timed, kind, _ = run_reference_cpu(rp_h, col_h, x.cpu(), y.cpu(), seeds_c, sizes, bs, threads, 8, cb,
                                                      max_seconds=25.0, preroll=pre)
