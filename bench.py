@@ -577,6 +577,7 @@ def ours(args):
     run_batches(0, W)
     barrier()
     launches0 = lib.spp_launch_count()
+    replays0 = int(lib.spp_graph_replays())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
     for s in pipe.slots:
@@ -590,6 +591,7 @@ def ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(lib.spp_launch_count() - launches0)
+    replays = int(lib.spp_graph_replays()) - replays0
     if args.device_only:
         clocks.stop()
         if world > 1:
@@ -598,7 +600,7 @@ def ours(args):
             ms = float(t.item())
         if rank == 0:
             print(json.dumps({"device_only": True, "batches_per_s": round(world * K / (ms * 1e-3), 1),
-                              "us_per_batch": round(1000.0 * ms / K, 2), "launches": launches,
+                              "us_per_batch": round(1000.0 * ms / K, 2), "launches": launches, "graph_replays": replays,
                               "host_issue_us_per_batch": round(1e6 * t_issue / K, 2),
                               "env": {k: v for k, v in os.environ.items() if k.startswith("SPP_")}}), flush=True)
         if world > 1:
@@ -843,6 +845,7 @@ def ours(args):
                                      "consumer_blocked_us_total": None if blocked_us is None else round(blocked_us, 1),
                                      "consumer_blocked_batches": blocked_n}},
             "gpu_launches": launches,
+            "cuda_graph_replays": replays,
             "host_issue_us_per_batch": round(1e6 * t_issue / K, 2),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_gather (feature gather" + (", partitioned: local + cache + peer rows)" if P > 1 else ")"),

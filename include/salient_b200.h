@@ -50,6 +50,8 @@ int spp_tune(const char* key, int value);
 const char* spp_last_error(void);
 /* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
 uint64_t spp_launch_count(void);
+/* number of mini-batches issued as ONE CUDA-graph launch (spp_batch_job.job_dev set; SPP_GRAPH=0 disables) */
+uint64_t spp_graph_replays(void);
 
 /* ------------------------------------------------------------------------------------------
  * K4 -- feature gather.  Replaces serial_index (fast_sampler/fast_sampler.cpp:238-279) and,
@@ -272,6 +274,26 @@ int spp_sample_export_nids(const spp_sampler_ws* ws_host, int hop, void* n_id_ou
  * (spp_batch_enqueue) or by a per-device executor thread (spp_executor_*), so that a Python
  * consumer never spends its own time inside the CUDA driver.
  * ---------------------------------------------------------------------------------------- */
+/* Per-batch part of a job, resident in DEVICE memory (one block per in-flight slot).  When a job
+ * carries `job_dev`, every kernel of the launch sequence reads the batch's output pointers,
+ * capacities, seeds and RNG key from this block instead of from its launch parameters, so the
+ * whole sequence is captured ONCE per slot into a CUDA graph and replayed for every mini-batch:
+ * per batch the host writes the pinned copy `job_host` (+ the seeds into `seeds_stage_host`) and
+ * launches the graph, whose first nodes copy both to the device. */
+typedef struct spp_device_job {
+  int64_t* out_rowptr[SPP_MAX_HOPS];
+  int64_t* out_col[SPP_MAX_HOPS];
+  int64_t out_col_cap[SPP_MAX_HOPS];
+  int64_t* n_id_out;
+  void* x_out;
+  void* y_out;
+  int64_t* bucket_ids;
+  int64_t* perm;
+  const int64_t* seeds;
+  int64_t batch_size;
+  uint64_t rng_premixed;
+} spp_device_job;
+
 typedef struct spp_batch_job {
   spp_graph graph;
   spp_sampler_ws ws;
@@ -306,6 +328,14 @@ typedef struct spp_batch_job {
   int64_t* meta_host;              /* pinned int64[SPP_META_WORDS + SPP_MAX_PARTS + 2] or NULL  */
   void* stream;
   int64_t* gather_counters;        /* optional device int64[3]: rows served local / cache / peer */
+  /* graph replay (all optional; job_dev == NULL: plain stream launches) */
+  spp_device_job* job_dev;         /* device block of this slot                                  */
+  spp_device_job* job_host;        /* pinned host staging copy of it                             */
+  int64_t* seeds_stage_host;       /* pinned int64[batch_size_cap]: seeds_host is copied here    */
+  int64_t batch_size_cap;          /* largest batch_size this slot will see (grids are sized by  */
+                                   /* it); 0 = batch_size                                        */
+  int64_t out_col_bound[SPP_MAX_HOPS]; /* static upper bound of out_col_cap[h] (grid sizing);   */
+                                   /* 0 = out_col_cap[h]                                         */
 } spp_batch_job;
 
 /* issue every call of the job on the calling thread (asynchronous w.r.t. the GPU) */

@@ -25,7 +25,7 @@ META_EDGES0 = 12
 META_OVERFLOW = 24
 
 EXPORTED = [
-    "spp_abi_version", "spp_tune", "spp_last_error", "spp_launch_count",
+    "spp_abi_version", "spp_tune", "spp_last_error", "spp_launch_count", "spp_graph_replays",
     "spp_gather_rows", "spp_gather_rows_pitched", "spp_gather_partitioned",
     "spp_nid2partid", "spp_nid2localnid", "spp_nid_is_local",
     "spp_cache_index_bytes", "spp_cache_build_index", "spp_nid_is_cached", "spp_nid2cachenid",
@@ -69,6 +69,13 @@ class SamplerSizes(Structure):
                 ("hop_edges", c_int64 * SPP_MAX_HOPS)]
 
 
+class DeviceJob(Structure):
+    _fields_ = [("out_rowptr", c_void_p * SPP_MAX_HOPS), ("out_col", c_void_p * SPP_MAX_HOPS),
+                ("out_col_cap", c_int64 * SPP_MAX_HOPS), ("n_id_out", c_void_p), ("x_out", c_void_p),
+                ("y_out", c_void_p), ("bucket_ids", c_void_p), ("perm", c_void_p), ("seeds", c_void_p),
+                ("batch_size", c_int64), ("rng_premixed", c_uint64)]
+
+
 class BatchJob(Structure):
     _fields_ = [("graph", Graph), ("ws", SamplerWs),
                 ("seeds_host", c_void_p), ("seeds_dev", c_void_p), ("batch_size", c_int64),
@@ -81,7 +88,9 @@ class BatchJob(Structure):
                 ("fmap", FeatureMap), ("x_out", c_void_p), ("y_table", c_void_p), ("y_row_bytes", c_int64),
                 ("y_out", c_void_p), ("bucket_ids", c_void_p), ("perm", c_void_p), ("bucket_counts", c_void_p),
                 ("split_scratch", c_void_p), ("meta_host", c_void_p), ("stream", c_void_p),
-                ("gather_counters", c_void_p)]
+                ("gather_counters", c_void_p),
+                ("job_dev", c_void_p), ("job_host", c_void_p), ("seeds_stage_host", c_void_p),
+                ("batch_size_cap", c_int64), ("out_col_bound", c_int64 * SPP_MAX_HOPS)]
 
 
 class SalientB200Error(RuntimeError):
@@ -115,6 +124,7 @@ def load() -> ctypes.CDLL:
     L.spp_last_error.restype = c_char_p
     L.spp_tune.argtypes = [c_char_p, ci]
     L.spp_launch_count.restype = c_uint64
+    L.spp_graph_replays.restype = c_uint64
     L.spp_gather_rows.argtypes = [vp, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_rows_pitched.argtypes = [vp, i64, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_partitioned.argtypes = [POINTER(FeatureMap), i64, vp, ci, i64, vp, vp, vp, i64, vp, vp]

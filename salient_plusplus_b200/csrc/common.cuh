@@ -12,6 +12,7 @@ namespace spp {
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+void count_replay();
 int num_sms();
 
 // diagnostics (runtime.cu): event mark on `st` after an operation was issued; no-op unless a
@@ -52,7 +53,20 @@ bool ipc_imported(const void* p);
 int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batch_size, const int32_t* sizes,
                           int n_hops, int replace, uint64_t rng_seed, const spp_sampler_ws* ws,
                           int64_t* const* out_rowptr, int64_t* const* out_col, const int64_t* out_col_cap,
-                          int64_t* n_id_out, cudaStream_t st, bool* pending);
+                          int64_t* n_id_out, cudaStream_t st, bool* pending, const spp_device_job* job, bool want_nid);
+int sorter_attributes();
+int gather_attributes();
+// gather.cu / partition.cu: the same entry points with the per-batch outputs taken from a device job block
+int gather_rows_job(const void* table, int64_t table_pitch, int64_t row_bytes, const void* idx, int idx_is_64, int64_t n_idx,
+                    const int64_t* n_idx_dev, void* out, int64_t n_out_rows, cudaStream_t st, const spp_device_job* job,
+                    int job_mode);
+int gather_partitioned_job(const spp_feature_map* m, int64_t row_bytes, const void* n_id, int idx_is_64, int64_t n_idx,
+                           const int64_t* n_idx_dev, const int32_t* src_desc, void* out, int64_t n_out_rows,
+                           int64_t* counters, cudaStream_t st, const spp_device_job* job);
+int split_by_owner_job(const spp_feature_map* m, int use_cache, const void* n_id, int idx_is_64, int64_t n_max,
+                       const int64_t* n_dev, int64_t* bucket_ids, int64_t* perm, int64_t* bucket_counts, int32_t* scratch,
+                       cudaStream_t st, const spp_device_job* job);
+bool tracing_active();
 int join_relabel(cudaStream_t st, bool pending);
 
 #define SPP_CUDA(expr)                                        \

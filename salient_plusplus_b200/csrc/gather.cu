@@ -39,7 +39,33 @@ struct GatherParams {
   const int32_t* desc;           // optional per-row source descriptors written by spp_split_by_owner
                                  // (p >= 0: partition p, < 0: ~cache row): no book search, no probe
   unsigned long long* counters;  // [3] local / cache / peer rows (optional)
+  // graph replay: per-batch pointers come from the device job block (session.cu)
+  const spp_device_job* job;
+  int job_mode;                  // 1: out = job->x_out; 2 (labels): idx = job->seeds, out = job->y_out, n <= job->batch_size
 };
+
+struct GatherView {
+  const void* idx;
+  char* out;
+  int64_t n;
+};
+__device__ __forceinline__ GatherView gather_view(const GatherParams& prm) {
+  GatherView v{prm.idx, prm.out, prm.n_max};
+  if (prm.n_dev != nullptr) {
+    const int64_t nd = *prm.n_dev;
+    v.n = nd < v.n ? nd : v.n;
+  }
+  if (prm.job != nullptr) {
+    if (prm.job_mode == 1) {
+      v.out = reinterpret_cast<char*>(prm.job->x_out);
+    } else if (prm.job_mode == 2) {
+      v.idx = prm.job->seeds;
+      v.out = reinterpret_cast<char*>(prm.job->y_out);
+      v.n = prm.job->batch_size < v.n ? prm.job->batch_size : v.n;
+    }
+  }
+  return v;
+}
 
 // Resolution of one output row's source pointer, split so that its two dependent loads (the index
 // and, for remote rows, the dense cache map) can be issued a tile ahead of their use.
@@ -94,13 +120,10 @@ template <typename V, bool kPartitioned, typename IdxT>
 __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant__ GatherParams prm) {
   __shared__ const char* s_src[2][kRows];
   const int tid = threadIdx.x;
-  int64_t n = prm.n_max;
-  if (prm.n_dev != nullptr) {
-    int64_t nd = *prm.n_dev;
-    n = nd < n ? nd : n;
-  }
+  const GatherView gv = gather_view(prm);
+  const int64_t n = gv.n;
   const int64_t num_tiles = (n + kRows - 1) / kRows;
-  const IdxT* __restrict__ idx = reinterpret_cast<const IdxT*>(prm.idx);
+  const IdxT* __restrict__ idx = reinterpret_cast<const IdxT*>(gv.idx);
   const uint32_t vpr = prm.vpr, magic = prm.vpr_magic;
   const bool resolver = tid < kRows;  // warps 0 and 1
   unsigned long long cnt0 = 0, cnt1 = 0, cnt2 = 0;
@@ -156,7 +179,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
       load_id(tile + 2 * (int64_t)gridDim.x, r2);  // tile t+2: id load in flight
     }
     const uint32_t chunks = (uint32_t)rows * vpr;
-    V* __restrict__ dst = reinterpret_cast<V*>(prm.out + row0 * prm.row_bytes);
+    V* __restrict__ dst = reinterpret_cast<V*>(gv.out + row0 * prm.row_bytes);
     const char* const* src = s_src[buf];
     for (uint32_t base = tid; base < chunks; base += kGatherThreads * kUnroll) {
       V vals[kUnroll];
@@ -247,11 +270,8 @@ __global__ void __launch_bounds__(kBulkWarps * 32) k_gather_bulk(const __grid_co
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ uint64_t s_bar[kBulkWarps][kBulkMaxStages];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int64_t n = prm.n_max;
-  if (prm.n_dev != nullptr) {
-    const int64_t nd = *prm.n_dev;
-    n = nd < n ? nd : n;
-  }
+  const GatherView gv = gather_view(prm);
+  const int64_t n = gv.n;
   const uint32_t row_bytes = (uint32_t)prm.row_bytes;
   const uint32_t stage_bytes = (uint32_t)tile_rows * row_bytes;
   unsigned char* my = s_raw + (size_t)warp * stages * stage_bytes;
@@ -261,7 +281,7 @@ __global__ void __launch_bounds__(kBulkWarps * 32) k_gather_bulk(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  const IdxT* __restrict__ idx = reinterpret_cast<const IdxT*>(prm.idx);
+  const IdxT* __restrict__ idx = reinterpret_cast<const IdxT*>(gv.idx);
   const int64_t num_tiles = (n + tile_rows - 1) / tile_rows;
   const int64_t wglobal = (int64_t)blockIdx.x * kBulkWarps + warp;
   const int64_t wstride = (int64_t)gridDim.x * kBulkWarps;
@@ -320,7 +340,7 @@ __global__ void __launch_bounds__(kBulkWarps * 32) k_gather_bulk(const __grid_co
     if (lane == 0) {
       const int64_t row0 = tile * tile_rows;
       const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
-      bulk_s2g(prm.out + row0 * prm.row_bytes, my + (size_t)stage * stage_bytes, (uint32_t)rows * row_bytes);
+      bulk_s2g(gv.out + row0 * prm.row_bytes, my + (size_t)stage * stage_bytes, (uint32_t)rows * row_bytes);
       bulk_commit();
     }
     if (t_issue < num_tiles) {
@@ -354,6 +374,21 @@ static bool map_has_peer_tables(const GatherParams& prm) {
   for (int p = 0; p < prm.book.num_parts; ++p)
     if (p != prm.book.rank && prm.tables[p] != nullptr && ipc_imported(prm.tables[p])) return true;
   return false;
+}
+
+// opt-in shared-memory size of the bulk-copy flavour (once per device; also called before a launch
+// sequence is captured into a CUDA graph)
+int gather_attributes() {
+  static bool done[64] = {false};
+  int dev = 0;
+  SPP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || done[dev]) return 0;
+  SPP_CUDA(cudaFuncSetAttribute(k_gather_bulk<true, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SPP_CUDA(cudaFuncSetAttribute(k_gather_bulk<true, int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SPP_CUDA(cudaFuncSetAttribute(k_gather_bulk<false, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SPP_CUDA(cudaFuncSetAttribute(k_gather_bulk<false, int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  done[dev] = true;
+  return 0;
 }
 
 // decided by the A/B runs under profiles/ (r02_ab_gather_bulk_*.txt)
@@ -390,12 +425,7 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
     if (tile_rows < 1) tile_rows = 1;
     const size_t smem = (size_t)kBulkWarps * stages * tile_rows * prm.row_bytes;
     if (smem <= 200 * 1024) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        SPP_CUDA(cudaFuncSetAttribute(k_gather_bulk<kPartitioned, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SPP_CUDA(cudaFuncSetAttribute(k_gather_bulk<kPartitioned, int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-      }
+      if (int r = gather_attributes()) return r;
       const int64_t btiles = ceil_div(prm.n_max, tile_rows);
       const int64_t bmax = (int64_t)num_sms() * (cps > 0 ? cps : bcps);
       const int64_t want = ceil_div(btiles, kBulkWarps);
@@ -439,21 +469,16 @@ static int pick_vec_bytes(int64_t row_bytes, uintptr_t align_bits) {
 
 }  // namespace spp
 
-extern "C" {
+namespace spp {
 
-int spp_gather_rows(const void* table, int64_t row_bytes, const void* idx, int idx_is_64, int64_t n_idx,
-                    const int64_t* n_idx_dev, void* out, int64_t n_out_rows, void* stream) {
-  return spp_gather_rows_pitched(table, row_bytes, row_bytes, idx, idx_is_64, n_idx, n_idx_dev, out, n_out_rows, stream);
-}
-
-int spp_gather_rows_pitched(const void* table, int64_t table_pitch, int64_t row_bytes, const void* idx, int idx_is_64,
-                            int64_t n_idx, const int64_t* n_idx_dev, void* out, int64_t n_out_rows, void* stream) {
-  using namespace spp;
+int gather_rows_job(const void* table, int64_t table_pitch, int64_t row_bytes, const void* idx, int idx_is_64, int64_t n_idx,
+                    const int64_t* n_idx_dev, void* out, int64_t n_out_rows, cudaStream_t st, const spp_device_job* job,
+                    int job_mode) {
   if (row_bytes <= 0) return fail(SPP_EINVAL, "spp_gather_rows: row_bytes must be positive");
   if (table_pitch < row_bytes) return fail(SPP_EINVAL, "spp_gather_rows: table pitch smaller than the row");
   int64_t n = n_idx < n_out_rows ? n_idx : n_out_rows;
   if (n <= 0) return 0;
-  if (!table || !idx || !out) return fail(SPP_EINVAL, "spp_gather_rows: null pointer");
+  if (!table || (!job && (!idx || !out))) return fail(SPP_EINVAL, "spp_gather_rows: null pointer");
   GatherParams prm{};
   prm.table = (const char*)table;
   prm.idx = idx;
@@ -462,21 +487,25 @@ int spp_gather_rows_pitched(const void* table, int64_t table_pitch, int64_t row_
   prm.out = (char*)out;
   prm.row_bytes = row_bytes;
   prm.table_pitch = table_pitch;
-  int vb = pick_vec_bytes(row_bytes, (uintptr_t)table | (uintptr_t)out | (uintptr_t)table_pitch);
-  return launch_gather<false>(prm, vb, idx_is_64, (cudaStream_t)stream);
+  prm.job = job;
+  prm.job_mode = job ? job_mode : 0;
+  // with a job block the output address is not known to the host: torch allocations (512-byte
+  // aligned) are assumed; rows that need a narrower vector because of their size still get it
+  int vb = pick_vec_bytes(row_bytes, (uintptr_t)table | (job ? 0 : (uintptr_t)out) | (uintptr_t)table_pitch);
+  if (job && job_mode == 2 && vb > 8) vb = 8;  // label rows live at the tail of the int64 arena: 8-byte aligned only
+  return launch_gather<false>(prm, vb, idx_is_64, st);
 }
 
-int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const void* n_id, int idx_is_64,
-                           int64_t n_idx, const int64_t* n_idx_dev, const int32_t* src_desc, void* out,
-                           int64_t n_out_rows, int64_t* counters, void* stream) {
-  using namespace spp;
+int gather_partitioned_job(const spp_feature_map* m, int64_t row_bytes, const void* n_id, int idx_is_64, int64_t n_idx,
+                           const int64_t* n_idx_dev, const int32_t* src_desc, void* out, int64_t n_out_rows,
+                           int64_t* counters, cudaStream_t st, const spp_device_job* job) {
   if (!m) return fail(SPP_EINVAL, "spp_gather_partitioned: null feature map");
   if (m->num_parts < 1 || m->num_parts > SPP_MAX_PARTS || m->rank < 0 || m->rank >= m->num_parts)
     return fail(SPP_EINVAL, "spp_gather_partitioned: bad num_parts/rank (%d/%d)", m->num_parts, m->rank);
   if (row_bytes <= 0) return fail(SPP_EINVAL, "spp_gather_partitioned: row_bytes must be positive");
   int64_t n = n_idx < n_out_rows ? n_idx : n_out_rows;
   if (n <= 0) return 0;
-  if (!n_id || !out) return fail(SPP_EINVAL, "spp_gather_partitioned: null pointer");
+  if (!n_id || (!out && !job)) return fail(SPP_EINVAL, "spp_gather_partitioned: null pointer");
   if ((m->cache_index == nullptr) != (m->cache_table == nullptr))
     return fail(SPP_EINVAL, "spp_gather_partitioned: cache_index and cache_table must be given together");
   GatherParams prm{};
@@ -484,6 +513,8 @@ int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const vo
   prm.n_dev = n_idx_dev;
   prm.n_max = n;
   prm.out = (char*)out;
+  prm.job = job;
+  prm.job_mode = job ? 1 : 0;
   prm.row_bytes = row_bytes;
   prm.table_pitch = m->table_pitch > 0 ? m->table_pitch : row_bytes;
   prm.cache_pitch = m->cache_pitch > 0 ? m->cache_pitch : row_bytes;
@@ -491,7 +522,7 @@ int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const vo
     return fail(SPP_EINVAL, "spp_gather_partitioned: pitch smaller than the row");
   prm.book.num_parts = m->num_parts;
   prm.book.rank = m->rank;
-  uintptr_t align = (uintptr_t)out | (uintptr_t)prm.table_pitch | (uintptr_t)prm.cache_pitch;
+  uintptr_t align = (job ? 0 : (uintptr_t)out) | (uintptr_t)prm.table_pitch | (uintptr_t)prm.cache_pitch;
   for (int p = 0; p <= SPP_MAX_PARTS; ++p) prm.book.off[p] = p <= m->num_parts ? m->offsets[p] : m->offsets[m->num_parts];
   for (int p = 0; p < m->num_parts; ++p) {
     if (m->offsets[p + 1] < m->offsets[p]) return fail(SPP_EINVAL, "spp_gather_partitioned: offsets not sorted");
@@ -507,7 +538,29 @@ int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const vo
   align |= (uintptr_t)m->cache_table;
   prm.counters = (unsigned long long*)counters;
   int vb = pick_vec_bytes(row_bytes, align);
-  return launch_gather<true>(prm, vb, idx_is_64, (cudaStream_t)stream);
+  return launch_gather<true>(prm, vb, idx_is_64, st);
+}
+
+}  // namespace spp
+
+extern "C" {
+
+int spp_gather_rows(const void* table, int64_t row_bytes, const void* idx, int idx_is_64, int64_t n_idx,
+                    const int64_t* n_idx_dev, void* out, int64_t n_out_rows, void* stream) {
+  return spp_gather_rows_pitched(table, row_bytes, row_bytes, idx, idx_is_64, n_idx, n_idx_dev, out, n_out_rows, stream);
+}
+
+int spp_gather_rows_pitched(const void* table, int64_t table_pitch, int64_t row_bytes, const void* idx, int idx_is_64,
+                            int64_t n_idx, const int64_t* n_idx_dev, void* out, int64_t n_out_rows, void* stream) {
+  return spp::gather_rows_job(table, table_pitch, row_bytes, idx, idx_is_64, n_idx, n_idx_dev, out, n_out_rows,
+                              (cudaStream_t)stream, nullptr, 0);
+}
+
+int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const void* n_id, int idx_is_64,
+                           int64_t n_idx, const int64_t* n_idx_dev, const int32_t* src_desc, void* out,
+                           int64_t n_out_rows, int64_t* counters, void* stream) {
+  return spp::gather_partitioned_job(m, row_bytes, n_id, idx_is_64, n_idx, n_idx_dev, src_desc, out, n_out_rows, counters,
+                                     (cudaStream_t)stream, nullptr);
 }
 
 }  // extern "C"

@@ -165,6 +165,7 @@ struct SplitParams {
   uint32_t* class_start; // [kClasses + 1]
   int32_t* desc;         // [n_max] per-node source descriptor: p >= 0 -> partition p, < 0 -> ~cache row
   int64_t tiles_max;
+  const spp_device_job* job;  // graph replay: bucket_ids / perm come from the device job block
 };
 
 __device__ __forceinline__ int64_t split_n(const SplitParams& p) {
@@ -249,6 +250,8 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_scatter(const __grid_co
   const IdxT* __restrict__ ids = reinterpret_cast<const IdxT*>(prm.n_id);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int P = prm.book.num_parts;
+  int64_t* const bucket_ids = prm.job ? prm.job->bucket_ids : prm.bucket_ids;
+  int64_t* const perm = prm.job ? prm.job->perm : prm.perm;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
     if (threadIdx.x < kClasses)
@@ -268,8 +271,8 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_scatter(const __grid_co
       if (valid) {
         uint32_t pos = s_run[c] + rank_in_warp;
         for (int w = 0; w < warp; ++w) pos += s_warpcnt[w][c];
-        prm.bucket_ids[pos] = (d < 0) ? (int64_t)(~d) : (int64_t)ids[i];
-        prm.perm[i] = (int64_t)pos;
+        bucket_ids[pos] = (d < 0) ? (int64_t)(~d) : (int64_t)ids[i];
+        perm[i] = (int64_t)pos;
       }
       __syncthreads();
       if (threadIdx.x < kClasses) {
@@ -387,8 +390,17 @@ int64_t spp_split_scratch_words(int64_t n_max) {
 int spp_split_by_owner(const spp_feature_map* m, int use_cache, const void* n_id, int idx_is_64, int64_t n_max,
                        const int64_t* n_dev, int64_t* bucket_ids, int64_t* perm, int64_t* bucket_counts,
                        int32_t* scratch, void* stream) {
-  using namespace spp;
-  cudaStream_t st = (cudaStream_t)stream;
+  return spp::split_by_owner_job(m, use_cache, n_id, idx_is_64, n_max, n_dev, bucket_ids, perm, bucket_counts, scratch,
+                                 (cudaStream_t)stream, nullptr);
+}
+
+}  // extern "C"
+
+namespace spp {
+
+int split_by_owner_job(const spp_feature_map* m, int use_cache, const void* n_id, int idx_is_64, int64_t n_max,
+                       const int64_t* n_dev, int64_t* bucket_ids, int64_t* perm, int64_t* bucket_counts, int32_t* scratch,
+                       cudaStream_t st, const spp_device_job* job) {
   if (!m) return fail(SPP_EINVAL, "spp_split_by_owner: null feature map");
   SplitParams prm{};
   if (int r = fill_book(prm.book, m->offsets, m->num_parts, m->rank, "spp_split_by_owner")) return r;
@@ -397,7 +409,7 @@ int spp_split_by_owner(const spp_feature_map* m, int use_cache, const void* n_id
   if (use_cache && !m->cache_index) return fail(SPP_EINVAL, "spp_split_by_owner: use_cache without a cache index");
   if (m->local_parts) prm.book.local_mask = m->local_parts | (1u << m->rank);
   if (n_max < 0) return fail(SPP_EINVAL, "spp_split_by_owner: negative n_max");
-  if (n_max > 0 && (!n_id || !bucket_ids || !perm)) return fail(SPP_EINVAL, "spp_split_by_owner: null pointer");
+  if (n_max > 0 && (!n_id || (!job && (!bucket_ids || !perm)))) return fail(SPP_EINVAL, "spp_split_by_owner: null pointer");
   if (n_max >= (1ll << 32)) return fail(SPP_EUNSUPPORTED, "spp_split_by_owner: n_max too large");
   prm.n_id = n_id;
   prm.n_dev = n_dev;
@@ -405,6 +417,7 @@ int spp_split_by_owner(const spp_feature_map* m, int use_cache, const void* n_id
   prm.cache = make_cache_index(use_cache ? m->cache_index : nullptr, m->cache_index_nodes);
   prm.bucket_ids = bucket_ids;
   prm.perm = perm;
+  prm.job = job;
   prm.bucket_counts = bucket_counts;
   prm.tiles_max = ceil_div(n_max > 0 ? n_max : 1, kSplitTile);
   prm.desc = scratch;
@@ -423,4 +436,4 @@ int spp_split_by_owner(const spp_feature_map* m, int use_cache, const void* n_id
   return 0;
 }
 
-}  // extern "C"
+}  // namespace spp

@@ -12,6 +12,7 @@
 namespace spp {
 
 static thread_local char g_err[512] = "";
+static std::atomic<int> g_trace_on{0};
 static std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -27,7 +28,10 @@ int cuda_fail(cudaError_t e, const char* what) {
   return (int)e;
 }
 
-void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)(int64_t)n, std::memory_order_relaxed); }
+static std::atomic<uint64_t> g_replays{0};
+void count_replay() { g_replays.fetch_add(1, std::memory_order_relaxed); }
+bool tracing_active() { return g_trace_on.load(std::memory_order_relaxed) != 0; }
 
 int num_sms() {
   static int sms[64] = {0};
@@ -52,7 +56,6 @@ struct TraceMark {
   cudaStream_t stream;
   cudaEvent_t ev;
 };
-static std::atomic<int> g_trace_on{0};
 static std::mutex g_trace_mu;
 static std::vector<TraceMark> g_trace;
 static size_t g_trace_cap = 0;
@@ -174,6 +177,7 @@ int spp_tune(const char* key, int value) {
 int spp_abi_version(void) { return SPP_ABI_VERSION; }
 const char* spp_last_error(void) { return spp::g_err; }
 uint64_t spp_launch_count(void) { return spp::g_launches.load(std::memory_order_relaxed); }
+uint64_t spp_graph_replays(void) { return spp::g_replays.load(std::memory_order_relaxed); }
 
 // ---- CUDA IPC ---------------------------------------------------------------------------------
 // The feature partition of every rank is exported once at set-up; peers map it and the gather

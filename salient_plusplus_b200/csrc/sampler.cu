@@ -82,10 +82,14 @@ __device__ __forceinline__ uint32_t table_find(const Table& t, int32_t key) {
 // ------------------------------------------------------------------------------------------------
 // seeds: n_ids[i] = seeds[i]; map[seed] = LAST position of that seed (sample_cpu.hpp:13-19)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_seeds_init(const int64_t* __restrict__ seeds, int64_t bs,
+__global__ void __launch_bounds__(1024) k_seeds_init(const spp_device_job* job, const int64_t* __restrict__ seeds, int64_t bs,
                                                      int32_t* __restrict__ n_ids, Table tab,
                                                      int64_t* __restrict__ meta) {
   const int tid = threadIdx.x;
+  if (job != nullptr) {
+    seeds = job->seeds;
+    bs = job->batch_size;
+  }
   for (int64_t i = tid; i < bs; i += blockDim.x) {
     const int32_t key = (int32_t)seeds[i];
     n_ids[i] = key;
@@ -204,9 +208,25 @@ struct HopParams {
   int32_t fanout;
   int32_t replace;
   int32_t bitmap_rows;  // != 0: rows longer than 32 go (un-relabelled) to k_sort_rows_bitmap
+  // When set, the per-batch pointers / capacities / RNG key are read from this device-resident
+  // block instead of the kernel parameters, so that a captured CUDA graph of the launch sequence
+  // can be replayed for every mini-batch of a slot (session.cu).
+  const spp_device_job* job;
 };
 
+__device__ __forceinline__ int64_t* hop_out_rowptr(const HopParams& p) { return p.job ? p.job->out_rowptr[p.hop] : p.out_rowptr; }
+__device__ __forceinline__ int64_t* hop_out_col(const HopParams& p) { return p.job ? p.job->out_col[p.hop] : p.out_col; }
+__device__ __forceinline__ int64_t hop_max_edges(const HopParams& p) { return p.job ? p.job->out_col_cap[p.hop] : p.max_edges; }
+__device__ __forceinline__ uint64_t hop_rng_key(const HopParams& p) { return p.job ? p.job->rng_premixed : p.premixed; }
+#define SPP_HOP_LOCALS                                  \
+  int64_t* const o_rowptr = hop_out_rowptr(prm);        \
+  int64_t* const o_col = hop_out_col(prm);              \
+  const int64_t o_cap = hop_max_edges(prm);             \
+  const uint64_t o_seed = hop_rng_key(prm);             \
+  (void)o_rowptr; (void)o_col; (void)o_cap; (void)o_seed;
+
 __global__ void __launch_bounds__(kScanThreads) k_hop_count_scan(const __grid_constant__ HopParams prm) {
+  SPP_HOP_LOCALS
   __shared__ uint64_t s_warp[kScanThreads / 32];
   __shared__ uint64_t s_bcast;
   __shared__ int64_t s_tile;
@@ -217,7 +237,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_count_scan(const __grid_co
   }
   const int64_t num_tiles = (T + kScanTile - 1) / kScanTile;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    prm.out_rowptr[0] = 0;
+    o_rowptr[0] = 0;
     prm.meta[kMetaWork] = 0;
     prm.meta[kMetaWork2] = 0;
     if (T == 0) prm.meta[SPP_META_EDGES(prm.hop)] = 0;
@@ -255,7 +275,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_count_scan(const __grid_co
     for (int q = 0; q < kScanItems; ++q) {
       const int64_t i = i0 + q;
       run += c[q];
-      if (i < T) prm.out_rowptr[i + 1] = (int64_t)run;
+      if (i < T) o_rowptr[i + 1] = (int64_t)run;
     }
     if (tile == num_tiles - 1 && threadIdx.x == 0) prm.meta[SPP_META_EDGES(prm.hop)] = (int64_t)(base + total);
   }
@@ -270,20 +290,21 @@ __device__ __forceinline__ int32_t load_col(const void* col, int64_t e) {
   else return __ldg(reinterpret_cast<const int32_t*>(col) + e);
 }
 
-__device__ __forceinline__ void emit_candidate(const HopParams& prm, int32_t node, uint32_t Tbase, int64_t p) {
+__device__ __forceinline__ void emit_candidate(const HopParams& prm, int64_t* out_col, int32_t node, uint32_t Tbase, int64_t p) {
   const uint32_t slot = table_insert(prm.tab, node);
   atomicMax(prm.tab.w + 2 * (size_t)slot + 1, ~(Tbase + (uint32_t)p));
-  prm.out_col[p] = (int64_t)slot;
+  out_col[p] = (int64_t)slot;
 }
 
 // kMode 1: with replacement; 2: without replacement (Floyd).  (Full neighbourhood is edge parallel:
 // k_hop_sample_edges below.)
 template <int kMode, int G, int PPL, bool kCol64>
 __global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_constant__ HopParams prm) {
+  SPP_HOP_LOCALS
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
   if (T > prm.max_targets) T = prm.max_targets;
   const int64_t E = prm.meta[SPP_META_EDGES(prm.hop)];
-  if (E > prm.max_edges || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) {
+  if (E > o_cap || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) {
     if (blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_OVERFLOW] = 1;
     return;
   }
@@ -304,13 +325,13 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_cons
     if (valid) {
       start = prm.tgt_start[i];
       deg = prm.tgt_deg[i];
-      p0 = prm.out_rowptr[i];
+      p0 = o_rowptr[i];
     }
     if constexpr (kMode == 1) {
       const int32_t c = deg > 0 ? k : 0;
       for (int32_t j = gl; j < c; j += G) {
-        const uint32_t pick = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)j), (uint32_t)deg);
-        emit_candidate(prm, load_col<kCol64>(prm.col, start + pick), Tbase, p0 + j);
+        const uint32_t pick = bounded(rand64(o_seed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)j), (uint32_t)deg);
+        emit_candidate(prm, o_col, load_col<kCol64>(prm.col, start + pick), Tbase, p0 + j);
       }
     } else {
       const bool need = valid && deg > k;
@@ -322,7 +343,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_cons
         myr[q] = 0;
         mypick[q] = 0xffffffffu;
         if (need && j < k)
-          myr[q] = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)j), (uint32_t)(basej + j) + 1u);
+          myr[q] = bounded(rand64(o_seed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)j), (uint32_t)(basej + j) + 1u);
       }
       if (__any_sync(kFullMask, need)) {
         // Floyd: step s draws t in [0, basej+s]; already chosen -> take basej+s instead.
@@ -356,7 +377,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_cons
 #pragma unroll
       for (int q = 0; q < PPL; ++q) {
         const int j = gl + G * q;
-        if (valid && j < c) emit_candidate(prm, node[q], Tbase, p0 + j);
+        if (valid && j < c) emit_candidate(prm, o_col, node[q], Tbase, p0 + j);
       }
     }
   }
@@ -368,10 +389,11 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample(const __grid_cons
 // consecutive lanes read consecutive col entries.
 template <bool kCol64>
 __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_edges(const __grid_constant__ HopParams prm) {
+  SPP_HOP_LOCALS
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
   if (T > prm.max_targets) T = prm.max_targets;
   const int64_t E = prm.meta[SPP_META_EDGES(prm.hop)];
-  if (E > prm.max_edges || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) {
+  if (E > o_cap || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) {
     if (blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_OVERFLOW] = 1;
     return;
   }
@@ -381,11 +403,11 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_edges(const __gri
     int64_t lo = 0, hi = T;  // out_rowptr[lo] <= p < out_rowptr[hi]
     while (hi - lo > 1) {
       const int64_t mid = (lo + hi) >> 1;
-      if (__ldg(prm.out_rowptr + mid) <= p) lo = mid;
+      if (__ldg(o_rowptr + mid) <= p) lo = mid;
       else hi = mid;
     }
-    const int64_t j = p - __ldg(prm.out_rowptr + lo);
-    emit_candidate(prm, load_col<kCol64>(prm.col, prm.tgt_start[lo] + j), Tbase, p);
+    const int64_t j = p - __ldg(o_rowptr + lo);
+    emit_candidate(prm, o_col, load_col<kCol64>(prm.col, prm.tgt_start[lo] + j), Tbase, p);
   }
 }
 
@@ -393,13 +415,14 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_edges(const __gri
 // 3. order-preserving compaction of first discoverers -> new local ids
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads) k_hop_compact(const __grid_constant__ HopParams prm) {
+  SPP_HOP_LOCALS
   __shared__ uint64_t s_warp[kScanThreads / 32];
   __shared__ uint64_t s_bcast;
   __shared__ int64_t s_tile;
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
   if (T > prm.max_targets) T = prm.max_targets;
   int64_t E = prm.meta[SPP_META_EDGES(prm.hop)];
-  if (E > prm.max_edges || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) E = 0;  // overflow already flagged
+  if (E > o_cap || (uint64_t)T + (uint64_t)E >= 0xFFFFFFF0ull) E = 0;  // overflow already flagged
   const uint32_t Tbase = (uint32_t)T;
   const int64_t num_tiles = (E + kScanTile - 1) / kScanTile;
   if (E == 0 && blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_NODES(prm.hop + 1)] = T;
@@ -412,7 +435,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact(const __grid_const
     uint32_t flags = 0, cnt = 0;
     const uint64_t* tab64 = reinterpret_cast<const uint64_t*>(prm.tab.w);
 #pragma unroll
-    for (int q = 0; q < kScanItems; ++q) slot[q] = (p0 + q < E) ? (uint32_t)prm.out_col[p0 + q] : 0u;
+    for (int q = 0; q < kScanItems; ++q) slot[q] = (p0 + q < E) ? (uint32_t)o_col[p0 + q] : 0u;
 #pragma unroll
     for (int q = 0; q < kScanItems; ++q) ent[q] = __ldcg(tab64 + slot[q]);
 #pragma unroll
@@ -471,6 +494,7 @@ __device__ __forceinline__ int32_t group_bitonic_sort(int32_t v, int gl) {
 // every row has at most G entries (sampled hops with fanout <= 32)
 template <int G>
 __global__ void __launch_bounds__(kSampleThreads) k_relabel_sort_small(const __grid_constant__ HopParams prm) {
+  SPP_HOP_LOCALS
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
   if (T > prm.max_targets) T = prm.max_targets;
   if (prm.meta[SPP_META_OVERFLOW]) return;
@@ -484,16 +508,16 @@ __global__ void __launch_bounds__(kSampleThreads) k_relabel_sort_small(const __g
     int64_t p0 = 0;
     int n = 0;
     if (i < T) {
-      p0 = prm.out_rowptr[i];
-      n = (int)(prm.out_rowptr[i + 1] - p0);
+      p0 = o_rowptr[i];
+      n = (int)(o_rowptr[i + 1] - p0);
     }
     int32_t v = 0x7fffffff;
     if (gl < n) {
-      const uint32_t slot = (uint32_t)prm.out_col[p0 + gl];
+      const uint32_t slot = (uint32_t)o_col[p0 + gl];
       v = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
     }
     v = group_bitonic_sort<G>(v, gl);
-    if (gl < n) prm.out_col[p0 + gl] = (int64_t)v;
+    if (gl < n) o_col[p0 + gl] = (int64_t)v;
   }
 }
 
@@ -527,6 +551,7 @@ __device__ __forceinline__ void network_sort(T* a, int64_t n, int tid, int nthre
 // are relabelled in place and queued (row index into tgt_deg, count in meta[kMetaWork])
 constexpr int kGeneralWarps = 4;
 __global__ void __launch_bounds__(kGeneralWarps * 32) k_relabel_sort_general(const __grid_constant__ HopParams prm) {
+  SPP_HOP_LOCALS
   __shared__ int32_t s_buf[kGeneralWarps][kWarpSortCap];
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
   if (T > prm.max_targets) T = prm.max_targets;
@@ -536,16 +561,16 @@ __global__ void __launch_bounds__(kGeneralWarps * 32) k_relabel_sort_general(con
   const int64_t warps_total = (int64_t)gridDim.x * kGeneralWarps;
   int32_t* buf = s_buf[warp];
   for (int64_t i = warp_global; i < T; i += warps_total) {
-    const int64_t p0 = prm.out_rowptr[i];
-    const int64_t n = prm.out_rowptr[i + 1] - p0;
+    const int64_t p0 = o_rowptr[i];
+    const int64_t n = o_rowptr[i + 1] - p0;
     if (n <= 32) {
       int32_t v = 0x7fffffff;
       if (lane < n) {
-        const uint32_t slot = (uint32_t)prm.out_col[p0 + lane];
+        const uint32_t slot = (uint32_t)o_col[p0 + lane];
         v = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
       }
       v = group_bitonic_sort<32>(v, lane);
-      if (lane < n) prm.out_col[p0 + lane] = (int64_t)v;
+      if (lane < n) o_col[p0 + lane] = (int64_t)v;
     } else if (prm.bitmap_rows) {  // k_sort_rows_bitmap relabels and sorts the row with a whole CTA
       if (lane == 0) {
         const unsigned long long w = atomicAdd((unsigned long long*)(prm.meta + kMetaWork), 1ull);
@@ -553,17 +578,17 @@ __global__ void __launch_bounds__(kGeneralWarps * 32) k_relabel_sort_general(con
       }
     } else if (n <= kWarpSortCap) {
       for (int64_t j = lane; j < n; j += 32) {
-        const uint32_t slot = (uint32_t)prm.out_col[p0 + j];
+        const uint32_t slot = (uint32_t)o_col[p0 + j];
         buf[j] = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
       }
       __syncwarp();
       network_sort(buf, n, lane, 32, [] { __syncwarp(); });
-      for (int64_t j = lane; j < n; j += 32) prm.out_col[p0 + j] = (int64_t)buf[j];
+      for (int64_t j = lane; j < n; j += 32) o_col[p0 + j] = (int64_t)buf[j];
       __syncwarp();
     } else {
       for (int64_t j = lane; j < n; j += 32) {
-        const uint32_t slot = (uint32_t)prm.out_col[p0 + j];
-        prm.out_col[p0 + j] = (int64_t)(int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
+        const uint32_t slot = (uint32_t)o_col[p0 + j];
+        o_col[p0 + j] = (int64_t)(int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
       }
       if (lane == 0) {
         const unsigned long long w = atomicAdd((unsigned long long*)(prm.meta + kMetaWork), 1ull);
@@ -583,6 +608,7 @@ __global__ void __launch_bounds__(kGeneralWarps * 32) k_relabel_sort_general(con
 // k_sort_large_rows through the second work list, like every row when S exceeds both bitmaps.
 __global__ void __launch_bounds__(256) k_sort_rows_bitmap(const __grid_constant__ HopParams prm, const int64_t min_bits,
                                                           const int64_t cap_bits, const int last) {
+  SPP_HOP_LOCALS
   extern __shared__ uint32_t s_bits[];
   __shared__ uint32_t s_wsum[8];
   if (prm.meta[SPP_META_OVERFLOW]) return;
@@ -596,9 +622,9 @@ __global__ void __launch_bounds__(256) k_sort_rows_bitmap(const __grid_constant_
   const int per = (words + 255) / 256;  // bitmap words per thread in the enumeration
   for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
     const int64_t i = prm.tgt_deg[w];
-    const int64_t p0 = prm.out_rowptr[i];
-    const int64_t n = prm.out_rowptr[i + 1] - p0;
-    int64_t* row = prm.out_col + p0;
+    const int64_t p0 = o_rowptr[i];
+    const int64_t n = o_rowptr[i + 1] - p0;
+    int64_t* row = o_col + p0;
     bool dup = !mine;
     if (mine)
       for (int t = tid; t < words; t += 256) s_bits[t] = 0u;
@@ -646,14 +672,15 @@ __global__ void __launch_bounds__(256) k_sort_rows_bitmap(const __grid_constant_
 // one CTA per queued long row (comparison network).  second_list: rows handed on by
 // k_sort_rows_bitmap (already relabelled), otherwise the rows queued by k_relabel_sort_general
 __global__ void __launch_bounds__(256) k_sort_large_rows(const __grid_constant__ HopParams prm, const int second_list) {
+  SPP_HOP_LOCALS
   extern __shared__ int32_t s_big[];
   const int64_t work = prm.meta[second_list ? kMetaWork2 : kMetaWork];
   const int32_t* list = second_list ? reinterpret_cast<const int32_t*>(prm.tgt_start) : prm.tgt_deg;
   for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
     const int64_t i = list[w];
-    const int64_t p0 = prm.out_rowptr[i];
-    const int64_t n = prm.out_rowptr[i + 1] - p0;
-    int64_t* row = prm.out_col + p0;
+    const int64_t p0 = o_rowptr[i];
+    const int64_t n = o_rowptr[i + 1] - p0;
+    int64_t* row = o_col + p0;
     if (n <= kBlockSortSmemElems) {
       for (int64_t j = threadIdx.x; j < n; j += blockDim.x) s_big[j] = (int32_t)row[j];
       __syncthreads();
@@ -668,8 +695,9 @@ __global__ void __launch_bounds__(256) k_sort_large_rows(const __grid_constant__
 }
 
 template <typename OutT>
-__global__ void k_export_nids(const int32_t* __restrict__ n_ids, const int64_t* __restrict__ meta, int word,
-                              int64_t max_nodes, OutT* __restrict__ out) {
+__global__ void k_export_nids(const spp_device_job* job, const int32_t* __restrict__ n_ids, const int64_t* __restrict__ meta,
+                              int word, int64_t max_nodes, OutT* __restrict__ out) {
+  if (job != nullptr) out = reinterpret_cast<OutT*>(job->n_id_out);
   int64_t n = meta[word];
   if (n > max_nodes) n = max_nodes;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -707,6 +735,7 @@ struct FusedParams {
 template <bool kCol64>
 __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __grid_constant__ FusedParams fp) {
   const HopParams& prm = fp.h;
+  SPP_HOP_LOCALS
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
   if (T > prm.max_targets) T = prm.max_targets;
   const int k = prm.fanout;
@@ -758,7 +787,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __gri
       const bool need = valid && deg > k;
       const int32_t basej = deg - k;
       uint32_t myr = 0, mypick = 0xffffffffu;
-      if (need) myr = bounded(rand64(prm.premixed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)gl), (uint32_t)(basej + gl) + 1u);
+      if (need) myr = bounded(rand64(o_seed, (uint32_t)prm.hop, (uint64_t)i, (uint32_t)gl), (uint32_t)(basej + gl) + 1u);
       if (__any_sync(kFullMask, need)) {
 #pragma unroll 1
         for (int s = 0; s < k; ++s) {  // Floyd: t uniform on [0, basej+s]; taken already -> basej+s
@@ -816,6 +845,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
   __shared__ unsigned long long s_base;
   __shared__ int64_t s_tile;
   const HopParams& prm = fp.h;
+  SPP_HOP_LOCALS
   // first ticket: issued at once, in flight together with the meta loads.  The ticket counter
   // (tile_state[0]) was zeroed by this hop's k_hop_sample_fused, which precedes us in stream order.
   if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd((unsigned long long*)prm.tile_state, 1ull);
@@ -830,7 +860,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
   uint64_t* agg = prm.tile_state + 2;                                   // [2 + t] epoch | kept | new
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    prm.out_rowptr[0] = 0;
+    o_rowptr[0] = 0;
     if (V == 0) {
       prm.meta[SPP_META_EDGES(prm.hop)] = 0;
       prm.meta[SPP_META_NODES(prm.hop + 1)] = T;
@@ -929,7 +959,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
           }
           ++new_run;
         }
-        if (r == k - 1) prm.out_rowptr[row + 1] = (int64_t)kept_run;
+        if (r == k - 1) o_rowptr[row + 1] = (int64_t)kept_run;
         if (++r == k) {
           r = 0;
           ++row;
@@ -943,7 +973,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
         prm.meta[SPP_META_OVERFLOW] = 1;
         S = prm.max_nodes;
       }
-      if ((int64_t)kept_total > prm.max_edges) prm.meta[SPP_META_OVERFLOW] = 1;  // out_col too small
+      if ((int64_t)kept_total > o_cap) prm.meta[SPP_META_OVERFLOW] = 1;  // out_col too small
       prm.meta[SPP_META_EDGES(prm.hop)] = (int64_t)kept_total;
       prm.meta[SPP_META_NODES(prm.hop + 1)] = S;
     }
@@ -957,6 +987,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
 template <int G>
 __global__ void __launch_bounds__(kSampleThreads) k_relabel_sort_fused(const __grid_constant__ FusedParams fp) {
   const HopParams& prm = fp.h;
+  SPP_HOP_LOCALS
   int64_t T = prm.meta[SPP_META_NODES(prm.hop)];
   if (T > prm.max_targets) T = prm.max_targets;
   if (prm.meta[SPP_META_OVERFLOW]) return;
@@ -971,8 +1002,8 @@ __global__ void __launch_bounds__(kSampleThreads) k_relabel_sort_fused(const __g
     int64_t p0 = 0;
     int n = 0;
     if (i < T) {
-      p0 = prm.out_rowptr[i];
-      n = (int)(prm.out_rowptr[i + 1] - p0);
+      p0 = o_rowptr[i];
+      n = (int)(o_rowptr[i + 1] - p0);
     }
     int32_t v = 0x7fffffff;
     if (gl < n) {
@@ -980,7 +1011,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_relabel_sort_fused(const __g
       v = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
     }
     v = group_bitonic_sort<G>(v, gl);
-    if (gl < n) prm.out_col[p0 + gl] = (int64_t)v;
+    if (gl < n) o_col[p0 + gl] = (int64_t)v;
   }
 }
 
@@ -1017,8 +1048,9 @@ static Table make_table(const spp_sampler_ws* ws) {
 
 static HopParams make_params(const spp_graph* g, const spp_sampler_ws* ws, int hop, int32_t fanout, int replace,
                              uint64_t rng_seed, int64_t max_targets, int64_t max_edges, int64_t* out_rowptr,
-                             int64_t* out_col) {
+                             int64_t* out_col, const spp_device_job* job = nullptr) {
   HopParams p{};
+  p.job = job;
   p.rowptr = g->rowptr;
   p.col = g->col;
   p.n_ids = ws->n_ids;
@@ -1059,7 +1091,7 @@ static int reset_tiles(const spp_sampler_ws* ws, int64_t bound_items, cudaStream
 }
 
 static int launch_begin(const spp_graph* g, const int64_t* seeds, int64_t bs, const spp_sampler_ws* ws,
-                        cudaStream_t st) {
+                        cudaStream_t st, const spp_device_job* job = nullptr) {
   if (int r = check_ws(ws)) return r;
   if (!g || !g->rowptr) return fail(SPP_EINVAL, "sampler: null graph");  // col may be NULL when nnz == 0
   if (ws->table_direct && ws->table_slots < g->num_nodes)
@@ -1067,21 +1099,21 @@ static int launch_begin(const spp_graph* g, const int64_t* seeds, int64_t bs, co
                 (long long)g->num_nodes);
   if (bs < 0 || bs > ws->max_nodes) return fail(SPP_ECAPACITY, "sampler: batch_size %lld exceeds max_nodes %lld",
                                                  (long long)bs, (long long)ws->max_nodes);
-  if (bs > 0 && !seeds) return fail(SPP_EINVAL, "sampler: null seeds");
+  if (bs > 0 && !seeds && !job) return fail(SPP_EINVAL, "sampler: null seeds");
   SPP_CUDA(cudaMemsetAsync(ws->table, 0, (size_t)ws->table_slots * sizeof(uint64_t), st));
   trace_mark(kTrTableClear, 0, st);
-  k_seeds_init<<<1, 1024, 0, st>>>(seeds, bs, ws->n_ids, make_table(ws), ws->meta);
+  k_seeds_init<<<1, 1024, 0, st>>>(job, seeds, bs, ws->n_ids, make_table(ws), ws->meta);
   SPP_KERNEL_CHECK("k_seeds_init");
   trace_mark(kTrSeedsInit, 0, st);
   return 0;
 }
 
 static int launch_count(const spp_graph* g, int hop, int32_t fanout, int replace, int64_t max_targets,
-                        const spp_sampler_ws* ws, int64_t* out_rowptr, cudaStream_t st) {
+                        const spp_sampler_ws* ws, int64_t* out_rowptr, cudaStream_t st, const spp_device_job* job = nullptr) {
   if (hop < 0 || hop >= SPP_MAX_HOPS) return fail(SPP_EINVAL, "sampler: hop %d out of range", hop);
-  if (!out_rowptr) return fail(SPP_EINVAL, "sampler: null out_rowptr");
+  if (!out_rowptr && !job) return fail(SPP_EINVAL, "sampler: null out_rowptr");
   if (int r = reset_tiles(ws, max_targets, st)) return r;
-  HopParams p = make_params(g, ws, hop, fanout, replace, 0, max_targets, 0, out_rowptr, nullptr);
+  HopParams p = make_params(g, ws, hop, fanout, replace, 0, max_targets, 0, out_rowptr, nullptr, job);
   p.tile_state += kGeneralTileOffset;
   k_hop_count_scan<<<scan_grid(p.max_targets), kScanThreads, 0, st>>>(p);
   SPP_KERNEL_CHECK("k_hop_count_scan");
@@ -1095,15 +1127,29 @@ static void launch_sample_kernel(const HopParams& p, bool col64, int grid, cudaS
   else k_hop_sample<kMode, G, PPL, false><<<grid, kSampleThreads, 0, st>>>(p);
 }
 
+// opt-in shared-memory sizes of the CTA-per-row sorters (once per device; also called before a
+// launch sequence is captured into a CUDA graph)
+int sorter_attributes() {
+  static bool done[64] = {false};
+  int dev = 0;
+  SPP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || done[dev]) return 0;
+  SPP_CUDA(cudaFuncSetAttribute(k_sort_large_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((size_t)kBlockSortSmemElems * sizeof(int32_t))));
+  SPP_CUDA(cudaFuncSetAttribute(k_sort_rows_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  done[dev] = true;
+  return 0;
+}
+
 static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace, uint64_t rng_seed,
                        int64_t max_targets, int64_t max_edges, const spp_sampler_ws* ws, const int64_t* out_rowptr,
-                       int64_t* out_col, cudaStream_t st) {
+                       int64_t* out_col, cudaStream_t st, const spp_device_job* job = nullptr) {
   if (hop < 0 || hop >= SPP_MAX_HOPS) return fail(SPP_EINVAL, "sampler: hop %d out of range", hop);
-  if (!out_rowptr || (!out_col && max_edges > 0)) return fail(SPP_EINVAL, "sampler: null output");
+  if (!job && (!out_rowptr || (!out_col && max_edges > 0))) return fail(SPP_EINVAL, "sampler: null output");
   if (fanout >= 0 && !replace && fanout > SPP_MAX_FANOUT)
     return fail(SPP_EUNSUPPORTED, "sampler: fanout %d > SPP_MAX_FANOUT (%d)", fanout, SPP_MAX_FANOUT);
   HopParams p = make_params(g, ws, hop, fanout, replace, rng_seed, max_targets, max_edges,
-                            const_cast<int64_t*>(out_rowptr), out_col);
+                            const_cast<int64_t*>(out_rowptr), out_col, job);
   p.tile_state += kGeneralTileOffset;
   const bool c64 = g->col_is_64 != 0;
   const int sms = num_sms();
@@ -1164,14 +1210,8 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
     SPP_KERNEL_CHECK("k_relabel_sort_general");
     trace_mark(kTrRelabel, hop, st);
     if (fanout < 0 || fanout > kWarpSortCap) {
-      static bool attr_set = false;
       const size_t smem = (size_t)kBlockSortSmemElems * sizeof(int32_t);
-      if (!attr_set) {
-        SPP_CUDA(cudaFuncSetAttribute(k_sort_large_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SPP_CUDA(cudaFuncSetAttribute(k_sort_rows_bitmap, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kBitsLarge / 8)));
-        attr_set = true;
-      }
+      if (int r = sorter_attributes()) return r;
       if (bitmap) {
         // small bitmap (16 KB: many CTAs per SM) for the usual batch, large one (200 KB) behind it;
         // whichever launch does not match the node count returns at once
@@ -1209,11 +1249,11 @@ static bool fused_ok(int32_t fanout, int replace, const spp_sampler_ws* ws) {
 static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_t rng_seed, int64_t max_targets,
                             int64_t max_edges, const spp_sampler_ws* ws, int64_t* out_rowptr, int64_t* out_col,
                             cudaStream_t st, int64_t cand_off = 0, cudaStream_t relabel_st = nullptr,
-                            cudaEvent_t fork_ev = nullptr) {
+                            cudaEvent_t fork_ev = nullptr, const spp_device_job* job = nullptr) {
   if (hop < 0 || hop >= SPP_MAX_HOPS) return fail(SPP_EINVAL, "sampler: hop %d out of range", hop);
-  if (!out_rowptr || (!out_col && max_edges > 0)) return fail(SPP_EINVAL, "sampler: null output");
+  if (!job && (!out_rowptr || (!out_col && max_edges > 0))) return fail(SPP_EINVAL, "sampler: null output");
   FusedParams fp{};
-  fp.h = make_params(g, ws, hop, fanout, 0, rng_seed, max_targets, max_edges, out_rowptr, out_col);
+  fp.h = make_params(g, ws, hop, fanout, 0, rng_seed, max_targets, max_edges, out_rowptr, out_col, job);
   const int64_t vmax = fp.h.max_targets * (int64_t)fanout;
   if (cand_off < 0 || (cand_off & 7) || cand_off + vmax > ws->cand_words)
     return fail(SPP_ECAPACITY, "sampler: cand buffer too small (%lld needed, %lld given)",
@@ -1274,14 +1314,14 @@ static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_
 }
 
 static int launch_export(const spp_sampler_ws* ws, int word, void* out, int out_is_64, int64_t max_nodes,
-                         cudaStream_t st) {
-  if (!out || max_nodes <= 0) return 0;
+                         cudaStream_t st, const spp_device_job* job = nullptr) {
+  if ((!out && !job) || max_nodes <= 0) return 0;
   int64_t cap = max_nodes < ws->max_nodes ? max_nodes : ws->max_nodes;
   int64_t ctas = ceil_div(cap, 256);
   int64_t lim = (int64_t)num_sms() * 8;
   int grid = (int)(ctas < lim ? ctas : lim);
-  if (out_is_64) k_export_nids<int64_t><<<grid, 256, 0, st>>>(ws->n_ids, ws->meta, word, cap, (int64_t*)out);
-  else k_export_nids<int32_t><<<grid, 256, 0, st>>>(ws->n_ids, ws->meta, word, cap, (int32_t*)out);
+  if (out_is_64) k_export_nids<int64_t><<<grid, 256, 0, st>>>(job, ws->n_ids, ws->meta, word, cap, (int64_t*)out);
+  else k_export_nids<int32_t><<<grid, 256, 0, st>>>(job, ws->n_ids, ws->meta, word, cap, (int32_t*)out);
   SPP_KERNEL_CHECK("k_export_nids");
   return 0;
 }
@@ -1295,12 +1335,14 @@ static int launch_export(const spp_sampler_ws* ws, int word, void* out, int out_
 int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batch_size, const int32_t* sizes,
                           int n_hops, int replace, uint64_t rng_seed, const spp_sampler_ws* ws,
                           int64_t* const* out_rowptr, int64_t* const* out_col, const int64_t* out_col_cap,
-                          int64_t* n_id_out, cudaStream_t st, bool* pending) {
+                          int64_t* n_id_out, cudaStream_t st, bool* pending, const spp_device_job* job, bool want_nid) {
+  // `job` != NULL: per-batch pointers, capacities, seeds and the RNG key are read by the kernels from
+  // that device block (graph replay); out_col_cap[] then only bounds grids and scratch ranges
   *pending = false;
   if (n_hops < 0 || n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_sample_minibatch: n_hops out of range");
   if (n_hops > 0 && (!sizes || !out_rowptr || !out_col || !out_col_cap))
     return fail(SPP_EINVAL, "spp_sample_minibatch: null argument");
-  if (int r = launch_begin(g, seeds, batch_size, ws, st)) return r;
+  if (int r = launch_begin(g, seeds, batch_size, ws, st, job)) return r;
   // one range of ws->cand per fused hop when they all fit (workspaces sized by spp_sampler_sizes
   // do); otherwise every hop reuses the start of the buffer and nothing is forked
   int64_t need = 0, T = batch_size;
@@ -1311,7 +1353,7 @@ int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batc
     T = next < ws->max_nodes ? next : ws->max_nodes;
   }
   const bool ranges = ws->cand != nullptr && need <= ws->cand_words;
-  AuxStreams* aux = (ranges && (pipeline_flags() & 1)) ? aux_streams(st) : nullptr;
+  AuxStreams* aux = (ranges && !job && (pipeline_flags() & 1)) ? aux_streams(st) : nullptr;
   // host-side frontier bounds (the device clamps to them and raises SPP_META_OVERFLOW)
   int64_t cand_off = 0;
   T = batch_size;
@@ -1319,7 +1361,7 @@ int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batc
     int64_t Tb = T < ws->max_targets ? T : ws->max_targets;
     if (fused_ok(sizes[h], replace, ws)) {
       if (int r = launch_hop_fused(g, h, sizes[h], rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st,
-                                   cand_off, aux ? aux->relabel : nullptr, aux ? aux->fork[h] : nullptr))
+                                   cand_off, aux ? aux->relabel : nullptr, aux ? aux->fork[h] : nullptr, job))
         return r;
       if (aux) *pending = true;
       if (ranges) cand_off += (Tb * (int64_t)sizes[h] + 7) & ~7ll;
@@ -1327,15 +1369,15 @@ int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batc
       // the general path rewrites table entries wholesale: earlier relabels must have finished
       if (int r = join_relabel(st, *pending)) return r;
       *pending = false;
-      if (int r = launch_count(g, h, sizes[h], replace, Tb, ws, out_rowptr[h], st)) return r;
-      if (int r = launch_fill(g, h, sizes[h], replace, rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st))
+      if (int r = launch_count(g, h, sizes[h], replace, Tb, ws, out_rowptr[h], st, job)) return r;
+      if (int r = launch_fill(g, h, sizes[h], replace, rng_seed, Tb, out_col_cap[h], ws, out_rowptr[h], out_col[h], st, job))
         return r;
     }
     int64_t next = T + out_col_cap[h];
     T = next < ws->max_nodes ? next : ws->max_nodes;
   }
-  if (n_id_out) {
-    if (int r = launch_export(ws, SPP_META_NODES(n_hops), n_id_out, 1, ws->max_nodes, st)) return r;
+  if (n_id_out || (job && want_nid)) {
+    if (int r = launch_export(ws, SPP_META_NODES(n_hops), n_id_out, 1, ws->max_nodes, st, job)) return r;
     trace_mark(kTrExport, 0, st);
   }
   return 0;
@@ -1441,7 +1483,7 @@ int spp_sample_minibatch(const spp_graph* g, const int64_t* seeds, int64_t batch
                          int64_t* n_id_out, void* stream) {
   bool pending = false;
   if (int r = spp::sample_minibatch_impl(g, seeds, batch_size, sizes, n_hops, replace, rng_seed, ws, out_rowptr, out_col,
-                                         out_col_cap, n_id_out, (cudaStream_t)stream, &pending))
+                                         out_col_cap, n_id_out, (cudaStream_t)stream, &pending, nullptr, false))
     return r;
   return spp::join_relabel((cudaStream_t)stream, pending);
 }

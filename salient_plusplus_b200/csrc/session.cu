@@ -7,6 +7,7 @@
 // job descriptor and later waits on the ticket.
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -17,29 +18,41 @@
 
 #include "common.cuh"
 
-extern "C" int spp_batch_enqueue(const spp_batch_job* j) {
-  using namespace spp;
-  if (!j) return fail(SPP_EINVAL, "spp_batch_enqueue: null job");
-  cudaStream_t st = (cudaStream_t)j->stream;
-  if (j->n_hops < 0 || j->n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_batch_enqueue: n_hops out of range");
-  const int64_t bs = j->batch_size;
+#include <map>
+
+namespace spp {
+
+// The launch sequence of one mini-batch.  `job` == NULL: plain stream launches with the per-batch
+// pointers in the kernel parameters.  `job` != NULL (graph capture): every kernel reads them from
+// the device job block; bounds used for grid sizing come from the static fields of `j`.
+static int issue_sequence(const spp_batch_job* j, cudaStream_t st, const spp_device_job* job) {
+  const bool replay = job != nullptr;
+  const int64_t bs = (replay && j->batch_size_cap > 0) ? j->batch_size_cap : j->batch_size;
   trace_mark(kTrBatchBegin, 0, st);
-  if (j->seeds_host && bs > 0) {
+  if (replay) {
+    SPP_CUDA(cudaMemcpyAsync(j->job_dev, j->job_host, sizeof(spp_device_job), cudaMemcpyHostToDevice, st));
+    if (j->seeds_host && bs > 0)
+      SPP_CUDA(cudaMemcpyAsync(j->seeds_dev, j->seeds_stage_host, (size_t)bs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  } else if (j->seeds_host && bs > 0) {
     if (!j->seeds_dev) return fail(SPP_EINVAL, "spp_batch_enqueue: seeds_dev missing");
     SPP_CUDA(cudaMemcpyAsync(j->seeds_dev, j->seeds_host, (size_t)bs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     trace_mark(kTrSeedsH2D, 0, st);
   }
+  int64_t caps[SPP_MAX_HOPS];
+  for (int h = 0; h < SPP_MAX_HOPS; ++h)
+    caps[h] = (replay && j->out_col_bound[h] > 0) ? j->out_col_bound[h] : j->out_col_cap[h];
   // the relabel/sort kernels may be left running on the side stream: nothing below reads out_col,
   // the join happens before the size block goes back to the host
   bool relabel_pending = false;
   if (int r = sample_minibatch_impl(&j->graph, j->seeds_dev, bs, j->sizes, j->n_hops, j->replace, j->rng_seed, &j->ws,
-                                    j->out_rowptr, j->out_col, j->out_col_cap, j->n_id_out, st, &relabel_pending))
+                                    j->out_rowptr, j->out_col, caps, j->n_id_out, st, &relabel_pending, job,
+                                    j->n_id_out != nullptr))
     return r;
   const int64_t* n_dev = j->ws.meta + SPP_META_NODES(j->n_hops);
   // optional: the feature + label gather on its own (lower-priority) stream
   cudaStream_t gst = st;
   AuxStreams* aux = nullptr;
-  if ((pipeline_flags() & 2) && (j->feature_mode || (j->y_table && bs > 0))) {
+  if (!replay && (pipeline_flags() & 2) && (j->feature_mode || (j->y_table && bs > 0))) {
     aux = aux_streams(st);
     if (aux) {
       SPP_CUDA(cudaEventRecord(aux->fork_gather, st));
@@ -48,27 +61,29 @@ extern "C" int spp_batch_enqueue(const spp_batch_job* j) {
     }
   }
   if (j->do_split) {
-    if (int r = spp_split_by_owner(&j->fmap, j->use_cache, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->bucket_ids,
-                                   j->perm, j->bucket_counts, j->split_scratch, st))
+    if (int r = split_by_owner_job(&j->fmap, j->use_cache, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->bucket_ids, j->perm,
+                                   j->bucket_counts, j->split_scratch, st, job))
       return r;
     trace_mark(kTrSplit, 0, st);
   }
   if (j->feature_mode == 1) {
-    if (int r = spp_gather_rows_pitched(j->table, j->table_pitch, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev,
-                                        j->x_out, j->ws.max_nodes, gst))
+    if (int r = gather_rows_job(j->table, j->table_pitch, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->x_out,
+                                j->ws.max_nodes, gst, job, 1))
       return r;
     trace_mark(kTrGather, 0, gst);
   } else if (j->feature_mode == 2) {
     // the owner split (when it ran) left one source descriptor per node in its scratch: the gather
     // reads them sequentially instead of probing the cache index a second time
-    if (int r = spp_gather_partitioned(&j->fmap, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev,
+    if (int r = gather_partitioned_job(&j->fmap, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev,
                                        j->do_split ? j->split_scratch : nullptr, j->x_out, j->ws.max_nodes,
-                                       j->gather_counters, gst))
+                                       j->gather_counters, gst, job))
       return r;
     trace_mark(kTrGather, 0, gst);
   }
   if (j->y_table && bs > 0) {
-    if (int r = spp_gather_rows(j->y_table, j->y_row_bytes, j->seeds_dev, 1, bs, nullptr, j->y_out, bs, gst)) return r;
+    if (int r = gather_rows_job(j->y_table, j->y_row_bytes, j->y_row_bytes, j->seeds_dev, 1, bs, nullptr, j->y_out, bs, gst,
+                                job, 2))
+      return r;
     trace_mark(kTrLabels, 0, gst);
   }
   if (gst != st) {
@@ -84,6 +99,135 @@ extern "C" int spp_batch_enqueue(const spp_batch_job* j) {
     trace_mark(kTrMetaD2H, 0, st);
   }
   return 0;
+}
+
+// ---- graph replay ------------------------------------------------------------------------------
+// One instantiated graph per stream (= per in-flight slot), valid for every job whose static part
+// (everything but the per-batch fields that travel through the device job block) is unchanged.
+struct GraphEntry {
+  spp_batch_job key;        // static part of the captured job
+  cudaGraphExec_t exec = nullptr;
+  uint64_t kernels = 0;     // kernel launches inside the graph (launch accounting)
+  bool broken = false;      // capture failed once on this stream: stay on plain launches
+};
+static std::mutex g_graph_mu;
+static std::map<cudaStream_t, GraphEntry> g_graphs;
+
+static int graph_mode_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPP_GRAPH");
+    v = (e && *e) ? atoi(e) : 1;
+  }
+  return v;
+}
+
+static void static_key(const spp_batch_job* j, spp_batch_job* k) {
+  memcpy(k, j, sizeof(*k));
+  k->seeds_host = j->seeds_host ? (const int64_t*)1 : nullptr;  // only whether seeds are staged from the host
+  if (j->seeds_host == nullptr) k->seeds_dev = nullptr;          // device seeds: pointer travels in the job block
+  k->batch_size = 0;
+  k->rng_seed = 0;
+  for (int h = 0; h < SPP_MAX_HOPS; ++h) {
+    k->out_rowptr[h] = nullptr;
+    k->out_col[h] = nullptr;
+    k->out_col_cap[h] = j->out_col_bound[h] > 0 ? 0 : j->out_col_cap[h];
+  }
+  k->n_id_out = j->n_id_out ? (int64_t*)1 : nullptr;
+  k->x_out = nullptr;
+  k->y_out = nullptr;
+  k->bucket_ids = nullptr;
+  k->perm = nullptr;
+  if (k->batch_size_cap <= 0) k->batch_size_cap = j->batch_size;
+}
+
+static void fill_device_job(const spp_batch_job* j, spp_device_job* d) {
+  for (int h = 0; h < SPP_MAX_HOPS; ++h) {
+    d->out_rowptr[h] = j->out_rowptr[h];
+    d->out_col[h] = j->out_col[h];
+    d->out_col_cap[h] = j->out_col_cap[h];
+  }
+  d->n_id_out = j->n_id_out;
+  d->x_out = j->x_out;
+  d->y_out = j->y_out;
+  d->bucket_ids = j->bucket_ids;
+  d->perm = j->perm;
+  d->seeds = j->seeds_dev;
+  d->batch_size = j->batch_size;
+  d->rng_premixed = premix_seed(j->rng_seed);
+}
+
+static int enqueue_replay(const spp_batch_job* j, cudaStream_t st, bool* done) {
+  *done = false;
+  spp_batch_job key;
+  static_key(j, &key);
+  GraphEntry* e;
+  {
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    e = &g_graphs[st];
+  }
+  if (e->broken) return 0;
+  bool hit = e->exec != nullptr && j->batch_size <= e->key.batch_size_cap;
+  if (hit) {
+    const int64_t cap_have = e->key.batch_size_cap;
+    key.batch_size_cap = cap_have;  // a smaller batch replays the graph captured for the larger cap
+    hit = memcmp(&e->key, &key, sizeof(key)) == 0;
+    if (!hit) static_key(j, &key);
+  }
+  if (!hit) {
+    if (e->exec) {
+      cudaGraphExecDestroy(e->exec);
+      e->exec = nullptr;
+    }
+    if (int r = sorter_attributes()) return r;
+    if (int r = gather_attributes()) return r;
+    spp_batch_job cap;
+    memcpy(&cap, j, sizeof(cap));
+    cap.batch_size_cap = key.batch_size_cap;
+    const uint64_t k0 = spp_launch_count();
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    if (ce == cudaSuccess) {
+      rc = issue_sequence(&cap, st, j->job_dev);
+      ce = cudaStreamEndCapture(st, &graph);
+    }
+    const uint64_t kernels = spp_launch_count() - k0;
+    count_launch(-(int)kernels);  // capture is not execution
+    if (ce == cudaSuccess && rc == 0 && graph) ce = cudaGraphInstantiate(&e->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (ce != cudaSuccess || rc != 0 || !e->exec) {
+      cudaGetLastError();
+      e->exec = nullptr;
+      e->broken = true;  // fall back to plain launches on this stream (reported by spp_graph_replays() staying 0)
+      return 0;
+    }
+    memcpy(&e->key, &key, sizeof(key));
+    e->kernels = kernels;
+  }
+  fill_device_job(j, j->job_host);
+  if (j->seeds_host && j->batch_size > 0) memcpy(j->seeds_stage_host, j->seeds_host, (size_t)j->batch_size * sizeof(int64_t));
+  SPP_CUDA(cudaGraphLaunch(e->exec, st));
+  count_launch((int)e->kernels);
+  count_replay();
+  *done = true;
+  return 0;
+}
+
+}  // namespace spp
+
+extern "C" int spp_batch_enqueue(const spp_batch_job* j) {
+  using namespace spp;
+  if (!j) return fail(SPP_EINVAL, "spp_batch_enqueue: null job");
+  cudaStream_t st = (cudaStream_t)j->stream;
+  if (j->n_hops < 0 || j->n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_batch_enqueue: n_hops out of range");
+  if (j->job_dev && j->job_host && (!j->seeds_host || j->seeds_stage_host) && graph_mode_enabled() && !tracing_active() &&
+      pipeline_flags() == 0) {
+    bool done = false;
+    if (int r = enqueue_replay(j, st, &done)) return r;
+    if (done) return 0;
+  }
+  return issue_sequence(j, st, nullptr);
 }
 
 namespace spp {

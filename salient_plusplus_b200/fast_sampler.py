@@ -657,6 +657,9 @@ class _Slot:
         self.job = None
         self.ticket = None
         self.cjob = BatchJob()
+        # graph replay: device-resident per-batch block + its pinned staging copy (spp_device_job)
+        self.job_dev = torch.zeros(ctypes.sizeof(_lib.DeviceJob) // 8, dtype=torch.int64, device=device)
+        self.job_host = torch.zeros(ctypes.sizeof(_lib.DeviceJob) // 8, dtype=torch.int64).pin_memory()
 
 
 _EXECUTORS: dict = {}
@@ -958,6 +961,13 @@ class Session:
         j.seeds_dev = slot.seeds.data_ptr()
         j.meta_host = slot.meta_host.data_ptr()
         j.stream = slot.stream.cuda_stream
+        # one CUDA graph per slot replays the whole launch sequence (SPP_GRAPH=0: plain launches)
+        j.job_dev = slot.job_dev.data_ptr()
+        j.job_host = slot.job_host.data_ptr()
+        j.seeds_stage_host = slot.seeds_host.data_ptr()
+        j.batch_size_cap = max(self._max_bs, 1)
+        if self._edge_bound is not None:
+            j.out_col_bound[0] = int(sz.hop_edges[0])
         if self._y is not None:
             j.y_table = self._y.data_ptr()
             j.y_row_bytes = self._y.size(-1) * self._y.element_size()

@@ -69,11 +69,15 @@ class MiniBatchPipeline:
                 s.counts = torch.zeros(SPP_MAX_PARTS + 2, dtype=torch.int64, device=self.device)
             s.counters = torch.zeros(3, dtype=torch.int64, device=self.device)  # local / cache / peer rows
             s.meta_host = torch.empty(SPP_META_WORDS, dtype=torch.int64).pin_memory()
+            s.job_dev = torch.zeros(ctypes.sizeof(_lib.DeviceJob) // 8, dtype=torch.int64, device=self.device)
+            s.job_host = torch.zeros(ctypes.sizeof(_lib.DeviceJob) // 8, dtype=torch.int64).pin_memory()
+            s.done = torch.cuda.Event()
+            s.in_flight = False
             s.job = self._make_job(s)
             self.slots.append(s)
         self.gather_events = None
 
-    def _make_job(self, s: _PipeSlot) -> BatchJob:
+    def _make_job(self, s: _PipeSlot, graph: bool = True) -> BatchJob:
         """The slot's spp_batch_job: the very descriptor a Session submits, with static outputs."""
         j = BatchJob()
         ctypes.memset(ctypes.byref(j), 0, ctypes.sizeof(j))
@@ -86,6 +90,8 @@ class MiniBatchPipeline:
             j.out_col[h] = s.cols[h].data_ptr()
         j.row_bytes = self.row_bytes
         j.stream = s.stream.cuda_stream
+        if graph:   # one CUDA graph per slot replays the launch sequence (what a Session's slot does)
+            j.job_dev, j.job_host, j.batch_size_cap = s.job_dev.data_ptr(), s.job_host.data_ptr(), self.bs
         if s.x is not None:
             j.x_out = s.x.data_ptr()
             if self.fm is not None:
@@ -144,8 +150,15 @@ class MiniBatchPipeline:
         s = self.slots[slot]
         if not time_gather:  # one C call, exactly what the Session's executor issues
             j = s.job
+            if s.in_flight:
+                # the pinned staging copy of the job block is read by the GPU when the slot's previous
+                # graph launch executes: wait for that batch before overwriting it (a Session only
+                # re-uses a slot after its batch was delivered)
+                s.done.synchronize()
             j.seeds_dev, j.batch_size, j.rng_seed = seeds_ptr, bs, rng_seed
             check(self.lib.spp_batch_enqueue(ctypes.byref(j)), "spp_batch_enqueue")
+            s.done.record(s.stream)
+            s.in_flight = True
             return None
         self.sample(s, seeds_ptr, bs, rng_seed)
         self.owner_split(s)

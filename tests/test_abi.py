@@ -122,7 +122,8 @@ int main(void) {
   if (s.max_nodes != 1081344) return 3;
   if (spp_gather_rows(0, 0, 0, 1, 1, 0, 0, 1, 0) == 0) return 4;   /* bad row_bytes must fail */
   printf("%s\\n", spp_last_error());
-  printf("sizes %d %d %d\\n", (int)sizeof(spp_batch_job), (int)sizeof(spp_feature_map), (int)sizeof(spp_sampler_ws));
+  printf("sizes %d %d %d %d\\n", (int)sizeof(spp_batch_job), (int)sizeof(spp_feature_map), (int)sizeof(spp_sampler_ws),
+         (int)sizeof(spp_device_job));
   return 0;
 }
 ''')
@@ -135,5 +136,6 @@ int main(void) {
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "row_bytes" in out.stdout
     # the ctypes mirrors have exactly the C layout
-    want = "sizes %d %d %d" % (ctypes.sizeof(_lib.BatchJob), ctypes.sizeof(_lib.FeatureMap), ctypes.sizeof(_lib.SamplerWs))
+    want = "sizes %d %d %d %d" % (ctypes.sizeof(_lib.BatchJob), ctypes.sizeof(_lib.FeatureMap), ctypes.sizeof(_lib.SamplerWs),
+                                  ctypes.sizeof(_lib.DeviceJob))
     assert want in out.stdout, (want, out.stdout)

@@ -370,3 +370,35 @@ def test_bulk_copy_gather_is_bit_exact(fs, dim, dtype, tile, stages):
     finally:
         for k_, v_ in (("gather_bulk", -1), ("bulk_tile", 4096), ("bulk_stages", 6)):
             _lib.tune(k_, v_)
+
+
+def test_session_batches_are_cuda_graph_replays(fs, data):
+    """Every mini-batch of a Session is ONE CUDA-graph launch (the per-batch pointers travel through
+    the device job block); ragged last batch and a second Session on the pooled slots replay the
+    same graphs; results are bit-exact against the oracle (same kernels as the plain path)."""
+    from salient_plusplus_b200 import _lib
+    if os.environ.get("SPP_GRAPH", "1") == "0" or os.environ.get("SPP_FORK", "0") != "0":
+        pytest.skip("graph replay switched off")
+    L = _lib.load()
+    rowptr, col, x, y, N = data
+    for rep in range(2):
+        idx = S.seeds(N, 64 * 7 + 13, seed=21 + rep)
+        cfg = fs.Config()
+        cfg.x_cpu, cfg.y, cfg.rowptr, cfg.col, cfg.idx = x, y, rowptr, col, idx
+        cfg.batch_size, cfg.sizes = 64, [15, 10, 5]
+        r0, k0 = int(L.spp_graph_replays()), _lib.launch_count()
+        sess = fs.Session(2, 4, cfg)
+        n = 0
+        while True:
+            b = sess.blocking_get_batch()
+            if b is None:
+                break
+            xb, yb, adjs, (st, en) = b
+            on, oa = O.multilayer_sample(idx[st:en].numpy(), cfg.sizes, rowptr.numpy(), col.numpy(), rng_mode=O.RNG_COUNTER,
+                                         rng_seed=O.session_rng_seed(en))
+            assert adjs_equal(adjs, oa) and torch.equal(xb.cpu(), x[torch.from_numpy(on)])
+            assert torch.equal(yb.cpu(), y[idx[st:en]])
+            n += 1
+        assert n == 8
+        assert int(L.spp_graph_replays()) - r0 == 8, "batches were not issued as graph launches"
+        assert _lib.launch_count() - k0 >= 8 * 12          # kernels inside the graphs are accounted for
