@@ -292,6 +292,7 @@ typedef struct spp_device_job {
   const int64_t* seeds;
   int64_t batch_size;
   uint64_t rng_premixed;
+  uint64_t scan_epoch;             /* tag of this batch's scan aggregates (hop h uses epoch + h)  */
 } spp_device_job;
 
 typedef struct spp_batch_job {

@@ -73,7 +73,7 @@ class DeviceJob(Structure):
     _fields_ = [("out_rowptr", c_void_p * SPP_MAX_HOPS), ("out_col", c_void_p * SPP_MAX_HOPS),
                 ("out_col_cap", c_int64 * SPP_MAX_HOPS), ("n_id_out", c_void_p), ("x_out", c_void_p),
                 ("y_out", c_void_p), ("bucket_ids", c_void_p), ("perm", c_void_p), ("seeds", c_void_p),
-                ("batch_size", c_int64), ("rng_premixed", c_uint64)]
+                ("batch_size", c_int64), ("rng_premixed", c_uint64), ("scan_epoch", c_uint64)]
 
 
 class BatchJob(Structure):

@@ -55,6 +55,7 @@ int sample_minibatch_impl(const spp_graph* g, const int64_t* seeds, int64_t batc
                           int64_t* const* out_rowptr, int64_t* const* out_col, const int64_t* out_col_cap,
                           int64_t* n_id_out, cudaStream_t st, bool* pending, const spp_device_job* job, bool want_nid);
 int sorter_attributes();
+uint64_t next_scan_epoch();
 int gather_attributes();
 // gather.cu / partition.cu: the same entry points with the per-batch outputs taken from a device job block
 int gather_rows_job(const void* table, int64_t table_pitch, int64_t row_bytes, const void* idx, int idx_is_64, int64_t n_idx,

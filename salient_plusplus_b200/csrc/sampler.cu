@@ -743,7 +743,14 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __gri
     if (blockIdx.x == 0 && threadIdx.x == 0) prm.meta[SPP_META_OVERFLOW] = 1;
     return;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) prm.tile_state[0] = 0;  // ticket counter of k_hop_compact_fused
+  if (blockIdx.x == 0) {
+    // ticket counter of k_hop_compact_fused, and every aggregate word that kernel will poll: it runs
+    // after this one in stream order, so no stale aggregate of an earlier launch (whatever its epoch
+    // tag, even after the 2^30 tags have wrapped) can ever be taken for a current one
+    if (threadIdx.x == 0) prm.tile_state[0] = 0;
+    const int64_t tiles = ((int64_t)T * k + kFusedTile - 1) / kFusedTile;
+    for (int64_t t = threadIdx.x; t < tiles; t += kSampleThreads) prm.tile_state[2 + t] = 0;
+  }
   const uint32_t Tbase = (uint32_t)T;
   const int lane = threadIdx.x & 31;
   const int gpw = 32 / k;                 // groups (targets) per warp
@@ -839,6 +846,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     if (fp.timeline != nullptr && threadIdx.x == 0) fp.timeline[tile * 8 + (i)] = globaltimer_ns(); \
   } while (0)
 
+// tag of this launch's tile aggregates: a kernel parameter for plain launches; under graph replay
+// (where parameters are frozen at capture time) it comes from the device job block, which the host
+// advances for every mini-batch
+__device__ __forceinline__ uint32_t scan_epoch(const FusedParams& fp) {
+  if (fp.h.job == nullptr) return fp.epoch;
+  return (uint32_t)((fp.h.job->scan_epoch + (uint64_t)fp.h.hop) % 0x3FFFFFFFull) + 1u;
+}
+
 __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid_constant__ FusedParams fp) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_red[kScanThreads / 32];
@@ -846,6 +861,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
   __shared__ int64_t s_tile;
   const HopParams& prm = fp.h;
   SPP_HOP_LOCALS
+  const uint32_t epoch = scan_epoch(fp);
   // first ticket: issued at once, in flight together with the meta loads.  The ticket counter
   // (tile_state[0]) was zeroed by this hop's k_hop_sample_fused, which precedes us in stream order.
   if (threadIdx.x == 0) s_tile = (int64_t)atomicAdd((unsigned long long*)prm.tile_state, 1ull);
@@ -911,7 +927,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
       total += x;
     }
     const uint32_t texcl = wbase + inc - mine;
-    if (threadIdx.x == 0) st_volatile_u64(agg + tile, ((uint64_t)fp.epoch << 32) | (uint64_t)total);
+    if (threadIdx.x == 0) st_volatile_u64(agg + tile, ((uint64_t)epoch << 32) | (uint64_t)total);
     SPP_STAMP(2);
     // Sum of the aggregates of every earlier tile (each is published independently of its owner's
     // own wait, so there is no serial chain).  Every thread reads its share of the flags at once
@@ -922,7 +938,7 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
       unsigned long long acc = 0;  // kept in the high 32 bits, new in the low 32 bits
       for (int64_t t = threadIdx.x; t < tile; t += kScanThreads) {
         uint64_t w = ld_volatile_u64(agg + t);
-        while ((uint32_t)(w >> 32) != fp.epoch) {
+        while ((uint32_t)(w >> 32) != epoch) {
           __nanosleep(64);
           w = ld_volatile_u64(agg + t);
         }
@@ -1234,7 +1250,11 @@ static int launch_fill(const spp_graph* g, int hop, int32_t fanout, int replace,
   return 0;
 }
 
-static std::atomic<uint32_t> g_epoch{1};
+// ONE process-wide counter feeds the tags of plain launches (one value per hop launch) and of
+// replayed jobs (SPP_MAX_HOPS consecutive values per mini-batch), so a tag cannot repeat on any
+// workspace before the counter has advanced by 2^30 - 1
+static std::atomic<uint64_t> g_epoch{1};
+uint64_t next_scan_epoch() { return g_epoch.fetch_add(SPP_MAX_HOPS, std::memory_order_relaxed); }
 static std::atomic<unsigned long long*> g_timeline{nullptr};
 
 static bool fused_ok(int32_t fanout, int replace, const spp_sampler_ws* ws) {
@@ -1266,7 +1286,7 @@ static int launch_hop_fused(const spp_graph* g, int hop, int32_t fanout, uint64_
   fp.timeline = g_timeline.load(std::memory_order_relaxed);
   // epochs stay in [1, 2^30): they can never equal the high word of a look-back state
   // (status << 30) left behind in the shared aggregate area by the general path
-  fp.epoch = (g_epoch.fetch_add(1, std::memory_order_relaxed) % 0x3FFFFFFFu) + 1u;
+  fp.epoch = (uint32_t)(g_epoch.fetch_add(1, std::memory_order_relaxed) % 0x3FFFFFFFull) + 1u;
   const bool c64 = g->col_is_64 != 0;
   const int sms = num_sms();
   const int G = fanout <= 4 ? 4 : fanout <= 8 ? 8 : fanout <= 16 ? 16 : 32;  // relabel/sort groups (power of two)

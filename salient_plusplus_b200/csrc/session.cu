@@ -155,6 +155,7 @@ static void fill_device_job(const spp_batch_job* j, spp_device_job* d) {
   d->seeds = j->seeds_dev;
   d->batch_size = j->batch_size;
   d->rng_premixed = premix_seed(j->rng_seed);
+  d->scan_epoch = next_scan_epoch();
 }
 
 static int enqueue_replay(const spp_batch_job* j, cudaStream_t st, bool* done) {

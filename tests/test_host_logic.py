@@ -67,7 +67,7 @@ def test_adj_and_batches():
 
 
 def test_struct_sizes_stable():
-    assert ctypes.sizeof(_lib.BatchJob) == 952 and ctypes.sizeof(_lib.DeviceJob) == 256
+    assert ctypes.sizeof(_lib.BatchJob) == 952 and ctypes.sizeof(_lib.DeviceJob) == 264
 
 
 def test_prepared_batch_keeps_four_fields_and_owner_fast_path():
