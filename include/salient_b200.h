@@ -298,7 +298,10 @@ typedef struct spp_device_job {
 typedef struct spp_batch_job {
   spp_graph graph;
   spp_sampler_ws ws;
-  const int64_t* seeds_host;       /* pinned host seeds of this batch (copied H2D) or NULL      */
+  const int64_t* seeds_host;       /* host seeds of this batch or NULL (device seeds).  Graph    */
+                                   /* replay copies them into seeds_stage_host on the CPU; plain */
+                                   /* launches hand them to cudaMemcpyAsync (pin them, or the    */
+                                   /* copy is staged synchronously by the driver)                */
   int64_t* seeds_dev;              /* device seeds (destination of the copy, or the input)      */
   int64_t batch_size;
   int32_t sizes[SPP_MAX_HOPS];

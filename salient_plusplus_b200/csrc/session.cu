@@ -60,16 +60,25 @@ static int issue_sequence(const spp_batch_job* j, cudaStream_t st, const spp_dev
       gst = aux->gather;
     }
   }
+  // an error after the fork must still join the side stream back into `st` (otherwise work queued on
+  // it would be left dangling behind the caller's synchronisation point)
+  auto bail = [&](int r) {
+    if (gst != st) {
+      cudaEventRecord(aux->join_gather, gst);
+      cudaStreamWaitEvent(st, aux->join_gather, 0);
+    }
+    return r;
+  };
   if (j->do_split) {
     if (int r = split_by_owner_job(&j->fmap, j->use_cache, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->bucket_ids, j->perm,
                                    j->bucket_counts, j->split_scratch, st, job))
-      return r;
+      return bail(r);
     trace_mark(kTrSplit, 0, st);
   }
   if (j->feature_mode == 1) {
     if (int r = gather_rows_job(j->table, j->table_pitch, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->x_out,
                                 j->ws.max_nodes, gst, job, 1))
-      return r;
+      return bail(r);
     trace_mark(kTrGather, 0, gst);
   } else if (j->feature_mode == 2) {
     // the owner split (when it ran) left one source descriptor per node in its scratch: the gather
@@ -77,13 +86,13 @@ static int issue_sequence(const spp_batch_job* j, cudaStream_t st, const spp_dev
     if (int r = gather_partitioned_job(&j->fmap, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev,
                                        j->do_split ? j->split_scratch : nullptr, j->x_out, j->ws.max_nodes,
                                        j->gather_counters, gst, job))
-      return r;
+      return bail(r);
     trace_mark(kTrGather, 0, gst);
   }
   if (j->y_table && bs > 0) {
     if (int r = gather_rows_job(j->y_table, j->y_row_bytes, j->y_row_bytes, j->seeds_dev, 1, bs, nullptr, j->y_out, bs, gst,
                                 job, 2))
-      return r;
+      return bail(r);
     trace_mark(kTrLabels, 0, gst);
   }
   if (gst != st) {

@@ -369,3 +369,34 @@ def test_side_stream_fork_is_bit_exact():
                        cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+def test_device_side_epoch_shuffle_feeds_a_session_without_host_seeds(fs, data):
+    """shufflers.py with device="cuda": the epoch permutation is drawn on the GPU, the Session reads
+    the seeds of every batch in place from HBM (no H2D), and the batches are bit-exact against the
+    oracle on those seeds; rank slices of the common permutation are disjoint and cover it."""
+    from salient_plusplus_b200.shufflers import DistributedShuffler, Shuffler
+    rowptr, col, x, y, N = data
+    train = torch.arange(0, N, 3)
+    sh = Shuffler(train, device="cuda")
+    sh.set_epoch(3)
+    a, b = sh.get_idx(), sh.get_idx()
+    assert a.is_cuda and torch.equal(a, b) and torch.equal(torch.sort(a).values.cpu(), train)
+    sh.set_epoch(4)
+    assert not torch.equal(sh.get_idx(), a)
+    ds = DistributedShuffler(train, 4, device="cuda")
+    parts = [ds.get_idx(r) for r in range(4)]
+    assert torch.equal(torch.sort(torch.cat(parts)).values.cpu(), train)
+    n = train.numel()
+    assert [p.numel() for p in parts] == [(n * (r + 1)) // 4 - (n * r) // 4 for r in range(4)]
+    idx = a[:64 * 3 + 5]
+    cfg = _config(fs, x, y, rowptr, col, idx)
+    sess = fs.Session(2, 4, cfg)
+    assert sess._idx is not None and sess._idx_host is None      # device-resident seeds, used in place
+    idx_h = idx.cpu()
+    for _ in range(4):
+        xb, yb, adjs, (st, en) = sess.blocking_get_batch()
+        on, oa = O.multilayer_sample(idx_h[st:en].numpy(), cfg.sizes, rowptr.numpy(), col.numpy(), rng_mode=O.RNG_COUNTER,
+                                     rng_seed=O.session_rng_seed(en))
+        assert adjs_equal(adjs, oa) and torch.equal(xb.cpu(), x[torch.from_numpy(on)]) and torch.equal(yb.cpu(), y[idx_h[st:en]])
+    assert sess.blocking_get_batch() is None
