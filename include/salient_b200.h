@@ -45,7 +45,8 @@ int spp_abi_version(void);
 /* run-time tunables (A/B tools, tests); defaults come from the SPP_* environment variables:
  *   "gather_ctas_per_sm" (0 = automatic), "gather_bulk" (-1 automatic, 0 never, 1 whenever the rows are
  *   multiples of 16 bytes: bulk-copy flavour of the gather), "bulk_tile" (bytes), "bulk_stages",
- *   "bulk_ctas_per_sm" */
+ *   "bulk_ctas_per_sm", "gather_split" (1: a batch's peer rows are fetched by their own launch on a
+ *   side stream, see spp_gather_by_class; 0: one fused launch) */
 int spp_tune(const char* key, int value);
 const char* spp_last_error(void);
 /* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
@@ -108,6 +109,17 @@ int spp_gather_partitioned(const spp_feature_map* map_host, int64_t row_bytes, c
                            int idx_is_64, int64_t n_idx, const int64_t* n_idx_dev,
                            const int32_t* src_desc, void* out, int64_t n_out_rows,
                            int64_t* counters, void* stream);
+
+/* K4 / K5 by source class.  After spp_split_by_owner every node has a position in bucket order;
+ * this gathers the rows of the buckets selected by class_mask (bit p: partition p, bit num_parts:
+ * cached rows) -- source side a dense walk over the buckets (bucket_ids + the split's scratch),
+ * destination side row inv[pos] of `out`.  A Session issues two of these on two streams, one for the
+ * buckets resident in local HBM and one for the buckets on peer GPUs, so that the NVLink-bound miss
+ * fetch overlaps the HBM-bound gather; together they write exactly what spp_gather_partitioned
+ * writes.  n_max is the n_max the split was called with. */
+int spp_gather_by_class(const spp_feature_map* map_host, int64_t row_bytes, const int64_t* bucket_ids,
+                        const int32_t* split_scratch, int64_t n_max, uint32_t class_mask, void* out,
+                        int64_t* counters, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2 -- RangePartitionBook kernels (fast_sampler/range_partition_book.cpp:89-107).

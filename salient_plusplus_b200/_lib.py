@@ -26,7 +26,7 @@ META_OVERFLOW = 24
 
 EXPORTED = [
     "spp_abi_version", "spp_tune", "spp_last_error", "spp_launch_count", "spp_graph_replays",
-    "spp_gather_rows", "spp_gather_rows_pitched", "spp_gather_partitioned",
+    "spp_gather_rows", "spp_gather_rows_pitched", "spp_gather_partitioned", "spp_gather_by_class",
     "spp_nid2partid", "spp_nid2localnid", "spp_nid_is_local",
     "spp_cache_index_bytes", "spp_cache_build_index", "spp_nid_is_cached", "spp_nid2cachenid",
     "spp_split_scratch_words", "spp_split_by_owner",
@@ -128,6 +128,7 @@ def load() -> ctypes.CDLL:
     L.spp_gather_rows.argtypes = [vp, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_rows_pitched.argtypes = [vp, i64, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_partitioned.argtypes = [POINTER(FeatureMap), i64, vp, ci, i64, vp, vp, vp, i64, vp, vp]
+    L.spp_gather_by_class.argtypes = [POINTER(FeatureMap), i64, vp, vp, i64, ctypes.c_uint32, vp, vp, vp]
     L.spp_nid2partid.argtypes = [POINTER(i64), ci, vp, i64, vp, vp]
     L.spp_nid2localnid.argtypes = [POINTER(i64), ci, ci, vp, i64, vp, vp]
     L.spp_nid_is_local.argtypes = [POINTER(i64), ci, ci, vp, i64, vp, vp]

@@ -43,6 +43,7 @@ struct Tunables {
   int bulk_tile;           // SPP_BULK_TILE            bytes per tile of the bulk-copy gather
   int bulk_stages;         // SPP_BULK_STAGES
   int bulk_ctas_per_sm;    // SPP_BULK_CTAS_PER_SM
+  int gather_split;        // SPP_GATHER_SPLIT         1: peer rows fetched by their own launch on a side stream
 };
 Tunables& tunables();
 
@@ -84,6 +85,19 @@ int join_relabel(cudaStream_t st, bool pending);
   } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Layout of spp_split_by_owner's scratch (partition.cu), shared with the gather-by-class kernel:
+//   [desc: n_max][inv: n_max][tile_hist: tiles * kSplitClasses][class_start: kSplitClasses + 1 ...]
+constexpr int kSplitTileRows = 2048;
+constexpr int kSplitClasses = SPP_MAX_PARTS + 1;
+static inline const int32_t* split_scratch_inv(const int32_t* scratch, int64_t n_max) { return scratch + n_max; }
+static inline const uint32_t* split_scratch_class_start(const int32_t* scratch, int64_t n_max) {
+  const int64_t tiles = ceil_div(n_max > 0 ? n_max : 1, kSplitTileRows);
+  return reinterpret_cast<const uint32_t*>(scratch + 2 * n_max) + tiles * kSplitClasses;
+}
+int gather_by_class_job(const spp_feature_map* m, int64_t row_bytes, const int64_t* bucket_ids, const int32_t* split_scratch,
+                        int64_t n_max, uint32_t class_mask, void* out, int64_t* counters, cudaStream_t st,
+                        const spp_device_job* job);
 
 // ---- device side -----------------------------------------------------------------------------
 constexpr uint32_t kFullMask = 0xffffffffu;

@@ -376,6 +376,150 @@ static bool map_has_peer_tables(const GatherParams& prm) {
   return false;
 }
 
+// ================================================================================================
+// Gather by source class.  After the owner split every node of the batch has a position `pos` in
+// bucket order (partition 0 .. P-1, then cached), bucket_ids[pos] = global id (or cache row) and
+// inv[pos] = its row in x.  This kernel serves ONE set of classes (a bit mask): the classes whose
+// rows live in this GPU's HBM (hosted partitions + replicated cache) or the classes that live on
+// peer GPUs.  The two launches run on two streams, so the NVLink-bound peer fetch (few CTAs, deep
+// queues) and the HBM-bound local gather overlap instead of sharing tiles in which every CTA waits
+// for its slowest, remote, rows.  Source side: dense walk over a bucket;
+// destination side: one row (>= 128 contiguous bytes for every BASELINE shape) per inv[pos].
+// ================================================================================================
+struct ClassGatherParams {
+  GatherParams g;              // tables, cache table, book (offsets), row / pitch sizes, out | job
+  const int64_t* bucket_ids;   // [n] (from the job block when g.job is set)
+  const int32_t* inv;          // [n]
+  const uint32_t* class_start; // [kSplitClasses + 1] exclusive prefix of the bucket sizes
+  uint32_t class_mask;         // bit c: this launch serves bucket c (c == num_parts: cached rows)
+};
+
+template <typename V>
+__global__ void __launch_bounds__(kGatherThreads) k_gather_classes(const __grid_constant__ ClassGatherParams cp) {
+  __shared__ const char* s_src[2][kRows];
+  __shared__ char* s_dst[2][kRows];
+  __shared__ uint32_t s_pref[kSplitClasses + 1];  // prefix of the served buckets' sizes
+  __shared__ uint32_t s_first[kSplitClasses];     // first position of every bucket
+  const GatherParams& prm = cp.g;
+  const int tid = threadIdx.x;
+  const int P = prm.book.num_parts;
+  if (tid == 0) {
+    uint32_t acc = 0;
+    for (int c = 0; c < kSplitClasses; ++c) {
+      const uint32_t lo = cp.class_start[c], hi = cp.class_start[c + 1];
+      s_first[c] = lo;
+      s_pref[c] = acc;
+      if ((cp.class_mask >> c) & 1u) acc += hi - lo;
+    }
+    s_pref[kSplitClasses] = acc;
+  }
+  __syncthreads();
+  const int64_t M = s_pref[kSplitClasses];
+  const int64_t num_tiles = (M + kRows - 1) / kRows;
+  char* const out = (prm.job != nullptr) ? reinterpret_cast<char*>(prm.job->x_out) : prm.out;
+  const int64_t* __restrict__ bucket_ids = (prm.job != nullptr) ? prm.job->bucket_ids : cp.bucket_ids;
+  const uint32_t vpr = prm.vpr, magic = prm.vpr_magic;
+  const bool resolver = tid < kRows;
+  unsigned long long cnt0 = 0, cnt1 = 0, cnt2 = 0;
+
+  // resolver state of one row: bucket, id / cache row and destination row (loads issued a tile ahead)
+  struct Row {
+    int64_t val = 0;
+    int32_t dst = 0;
+    int cls = -1;
+  };
+  auto load_row = [&](int64_t tile, Row& r) {
+    r.cls = -1;
+    const int64_t m = tile * kRows + tid;
+    if (tile < num_tiles && m < M) {
+      int c = 0;
+#pragma unroll
+      for (int q = 1; q < kSplitClasses; ++q)
+        if ((uint32_t)m >= s_pref[q]) c = q;
+      const uint32_t pos = s_first[c] + ((uint32_t)m - s_pref[c]);
+      r.val = bucket_ids[pos];
+      r.dst = cp.inv[pos];
+      r.cls = c;
+    }
+  };
+  auto publish = [&](const Row& r, int buf) {
+    const char* src = nullptr;
+    char* dst = nullptr;
+    int kind = -1;
+    if (r.cls >= 0) {
+      if (r.cls == P) {
+        src = prm.cache_table + r.val * prm.cache_pitch;
+        kind = 1;
+      } else {
+        src = prm.tables[r.cls] + (r.val - prm.book.off[r.cls]) * prm.table_pitch;
+        kind = book_is_local(prm.book, r.cls) ? 0 : 2;
+      }
+      dst = out + (int64_t)r.dst * prm.row_bytes;
+    }
+    s_src[buf][tid] = src;
+    s_dst[buf][tid] = dst;
+    if (prm.counters != nullptr) {
+      const uint32_t m0 = __ballot_sync(kFullMask, kind == 0), m1 = __ballot_sync(kFullMask, kind == 1),
+                     m2 = __ballot_sync(kFullMask, kind == 2);
+      if ((tid & 31) == 0) {
+        cnt0 += __popc(m0);
+        cnt1 += __popc(m1);
+        cnt2 += __popc(m2);
+      }
+    }
+  };
+
+  Row r1;
+  int64_t tile = blockIdx.x;
+  if (resolver) {
+    Row r0;
+    load_row(tile, r0);
+    load_row(tile + gridDim.x, r1);
+    publish(r0, 0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (; tile < num_tiles; tile += gridDim.x) {
+    const int64_t m0 = tile * kRows;
+    const int rows = (int)((M - m0) < kRows ? (M - m0) : kRows);
+    Row r2;
+    if (resolver) load_row(tile + 2 * (int64_t)gridDim.x, r2);
+    const uint32_t chunks = (uint32_t)rows * vpr;
+    const char* const* src = s_src[buf];
+    char* const* dst = s_dst[buf];
+    for (uint32_t base = tid; base < chunks; base += kGatherThreads * kUnroll) {
+      V vals[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t lc = base + u * kGatherThreads;
+        if (lc < chunks) {
+          const uint32_t r = magic ? __umulhi(lc, magic) : lc / vpr;
+          vals[u] = ld_nc_na(reinterpret_cast<const V*>(src[r]) + (lc - r * vpr));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t lc = base + u * kGatherThreads;
+        if (lc < chunks) {
+          const uint32_t r = magic ? __umulhi(lc, magic) : lc / vpr;
+          st_na(reinterpret_cast<V*>(dst[r]) + (lc - r * vpr), vals[u]);
+        }
+      }
+    }
+    if (resolver) {
+      publish(r1, buf ^ 1);
+      r1 = r2;
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  if (prm.counters != nullptr && resolver && (tid & 31) == 0) {
+    if (cnt0) atomicAdd(prm.counters + 0, cnt0);
+    if (cnt1) atomicAdd(prm.counters + 1, cnt1);
+    if (cnt2) atomicAdd(prm.counters + 2, cnt2);
+  }
+}
+
 // opt-in shared-memory size of the bulk-copy flavour (once per device; also called before a launch
 // sequence is captured into a CUDA graph)
 int gather_attributes() {
@@ -541,6 +685,74 @@ int gather_partitioned_job(const spp_feature_map* m, int64_t row_bytes, const vo
   return launch_gather<true>(prm, vb, idx_is_64, st);
 }
 
+
+int gather_by_class_job(const spp_feature_map* m, int64_t row_bytes, const int64_t* bucket_ids, const int32_t* split_scratch,
+                        int64_t n_max, uint32_t class_mask, void* out, int64_t* counters, cudaStream_t st,
+                        const spp_device_job* job) {
+  if (!m) return fail(SPP_EINVAL, "spp_gather_by_class: null feature map");
+  if (m->num_parts < 1 || m->num_parts > SPP_MAX_PARTS || m->rank < 0 || m->rank >= m->num_parts)
+    return fail(SPP_EINVAL, "spp_gather_by_class: bad num_parts/rank (%d/%d)", m->num_parts, m->rank);
+  if (row_bytes <= 0) return fail(SPP_EINVAL, "spp_gather_by_class: row_bytes must be positive");
+  if (n_max <= 0 || class_mask == 0) return 0;
+  if (!split_scratch || (!job && (!bucket_ids || !out))) return fail(SPP_EINVAL, "spp_gather_by_class: null pointer");
+  ClassGatherParams cp{};
+  GatherParams& prm = cp.g;
+  prm.out = (char*)out;
+  prm.job = job;
+  prm.job_mode = job ? 1 : 0;
+  prm.row_bytes = row_bytes;
+  prm.table_pitch = m->table_pitch > 0 ? m->table_pitch : row_bytes;
+  prm.cache_pitch = m->cache_pitch > 0 ? m->cache_pitch : row_bytes;
+  if (prm.table_pitch < row_bytes || prm.cache_pitch < row_bytes)
+    return fail(SPP_EINVAL, "spp_gather_by_class: pitch smaller than the row");
+  prm.book.num_parts = m->num_parts;
+  prm.book.rank = m->rank;
+  prm.book.local_mask = (1u << m->rank) | m->local_parts;
+  uintptr_t align = (job ? 0 : (uintptr_t)out) | (uintptr_t)row_bytes | (uintptr_t)prm.table_pitch;
+  bool peers = false;
+  for (int p = 0; p <= SPP_MAX_PARTS; ++p) prm.book.off[p] = p <= m->num_parts ? m->offsets[p] : m->offsets[m->num_parts];
+  for (int p = 0; p < m->num_parts; ++p) {
+    prm.tables[p] = (const char*)m->tables[p];
+    if ((class_mask >> p) & 1u) {
+      if (m->tables[p] == nullptr && m->offsets[p + 1] > m->offsets[p])
+        return fail(SPP_EINVAL, "spp_gather_by_class: partition %d has no table", p);
+      align |= (uintptr_t)m->tables[p];
+      peers = peers || (m->tables[p] != nullptr && ipc_imported(m->tables[p]));
+    }
+  }
+  if ((class_mask >> m->num_parts) & 1u) {
+    if (!m->cache_table) return fail(SPP_EINVAL, "spp_gather_by_class: cached bucket without a cache table");
+    align |= (uintptr_t)m->cache_table | (uintptr_t)prm.cache_pitch;
+  }
+  prm.cache_table = (const char*)m->cache_table;
+  prm.counters = (unsigned long long*)counters;
+  cp.bucket_ids = bucket_ids;
+  cp.inv = split_scratch_inv(split_scratch, n_max);
+  cp.class_start = split_scratch_class_start(split_scratch, n_max);
+  cp.class_mask = class_mask;
+  const int vb = pick_vec_bytes(row_bytes, align);
+  prm.vpr = (uint32_t)(row_bytes / vb);
+  if ((uint64_t)prm.vpr * kRows >= (1ull << 31)) return fail(SPP_EUNSUPPORTED, "spp_gather_by_class: row too wide");
+  const bool magic_ok = prm.vpr > 1 && (uint64_t)kRows * prm.vpr * prm.vpr < (1ull << 32);
+  prm.vpr_magic = magic_ok ? (uint32_t)(((1ull << 32) + prm.vpr - 1) / prm.vpr) : 0u;
+  const Tunables& tn = tunables();
+  // NVLink-bound launches need few CTAs (their rows are all remote: every byte in flight is a peer
+  // byte), HBM-bound ones the usual 4 per SM
+  int cps = tn.gather_ctas_per_sm > 0 ? tn.gather_ctas_per_sm : (peers ? 2 : 4);
+  const int64_t tiles = ceil_div(n_max, kRows);
+  const int64_t max_ctas = (int64_t)num_sms() * cps;
+  const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+  switch (vb) {
+    case 16: k_gather_classes<int4><<<grid, kGatherThreads, 0, st>>>(cp); break;
+    case 8: k_gather_classes<int2><<<grid, kGatherThreads, 0, st>>>(cp); break;
+    case 4: k_gather_classes<int><<<grid, kGatherThreads, 0, st>>>(cp); break;
+    case 2: k_gather_classes<short><<<grid, kGatherThreads, 0, st>>>(cp); break;
+    default: k_gather_classes<char><<<grid, kGatherThreads, 0, st>>>(cp); break;
+  }
+  SPP_KERNEL_CHECK("k_gather_classes");
+  return 0;
+}
+
 }  // namespace spp
 
 extern "C" {
@@ -561,6 +773,12 @@ int spp_gather_partitioned(const spp_feature_map* m, int64_t row_bytes, const vo
                            int64_t n_out_rows, int64_t* counters, void* stream) {
   return spp::gather_partitioned_job(m, row_bytes, n_id, idx_is_64, n_idx, n_idx_dev, src_desc, out, n_out_rows, counters,
                                      (cudaStream_t)stream, nullptr);
+}
+
+int spp_gather_by_class(const spp_feature_map* m, int64_t row_bytes, const int64_t* bucket_ids, const int32_t* split_scratch,
+                        int64_t n_max, uint32_t class_mask, void* out, int64_t* counters, void* stream) {
+  return spp::gather_by_class_job(m, row_bytes, bucket_ids, split_scratch, n_max, class_mask, out, counters,
+                                  (cudaStream_t)stream, nullptr);
 }
 
 }  // extern "C"

@@ -151,6 +151,7 @@ constexpr int kSplitThreads = 256;
 constexpr int kSplitRounds = 8;
 constexpr int kSplitTile = kSplitThreads * kSplitRounds;  // 2048
 constexpr int kClasses = SPP_MAX_PARTS + 1;               // 17
+static_assert(kSplitTile == kSplitTileRows && kClasses == kSplitClasses, "scratch layout shared with gather.cu");
 
 struct SplitParams {
   BookParams book;
@@ -164,6 +165,7 @@ struct SplitParams {
   uint32_t* tile_hist;   // [tiles_max][kClasses] -> exclusive per-class prefix over tiles
   uint32_t* class_start; // [kClasses + 1]
   int32_t* desc;         // [n_max] per-node source descriptor: p >= 0 -> partition p, < 0 -> ~cache row
+  int32_t* inv;          // [n_max] inverse of perm: inv[pos] = i (the gather-by-class kernels walk buckets)
   int64_t tiles_max;
   const spp_device_job* job;  // graph replay: bucket_ids / perm come from the device job block
 };
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(32 * kClasses) k_split_scan(const __grid_const
       if (q <= P) prm.bucket_counts[q] = (int64_t)s_total[q];
       acc += s_total[q];
     }
+    prm.class_start[kClasses] = acc;
     prm.bucket_counts[P + 1] = n;
   }
 }
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_scatter(const __grid_co
         for (int w = 0; w < warp; ++w) pos += s_warpcnt[w][c];
         bucket_ids[pos] = (d < 0) ? (int64_t)(~d) : (int64_t)ids[i];
         perm[i] = (int64_t)pos;
+        prm.inv[pos] = (int32_t)i;
       }
       __syncthreads();
       if (threadIdx.x < kClasses) {
@@ -384,7 +388,7 @@ int64_t spp_split_scratch_words(int64_t n_max) {
   using namespace spp;
   if (n_max < 0) n_max = 0;
   const int64_t tiles = ceil_div(n_max > 0 ? n_max : 1, kSplitTile);
-  return n_max + tiles * kClasses + (kClasses + 15) + 4;  // [desc n_max][tile_hist][class_start]
+  return 2 * n_max + tiles * kClasses + (kClasses + 15) + 4;  // [desc n_max][inv n_max][tile_hist][class_start]
 }
 
 int spp_split_by_owner(const spp_feature_map* m, int use_cache, const void* n_id, int idx_is_64, int64_t n_max,
@@ -421,7 +425,8 @@ int split_by_owner_job(const spp_feature_map* m, int use_cache, const void* n_id
   prm.bucket_counts = bucket_counts;
   prm.tiles_max = ceil_div(n_max > 0 ? n_max : 1, kSplitTile);
   prm.desc = scratch;
-  prm.tile_hist = reinterpret_cast<uint32_t*>(scratch + n_max);
+  prm.inv = scratch + n_max;
+  prm.tile_hist = reinterpret_cast<uint32_t*>(scratch + 2 * n_max);
   prm.class_start = prm.tile_hist + prm.tiles_max * kClasses;
   const int64_t cap = (int64_t)num_sms() * 8;
   const int grid = (int)(prm.tiles_max < cap ? prm.tiles_max : cap);

@@ -22,6 +22,15 @@
 
 namespace spp {
 
+// buckets (bit p: partition p) whose rows do not live on this GPU
+static uint32_t remote_class_mask(const spp_feature_map* m) {
+  const uint32_t local = (1u << m->rank) | m->local_parts;
+  uint32_t mask = 0;
+  for (int p = 0; p < m->num_parts; ++p)
+    if (!((local >> p) & 1u) && m->offsets[p + 1] > m->offsets[p]) mask |= 1u << p;
+  return mask;
+}
+
 // The launch sequence of one mini-batch.  `job` == NULL: plain stream launches with the per-batch
 // pointers in the kernel parameters.  `job` != NULL (graph capture): every kernel reads them from
 // the device job block; bounds used for grid sizing come from the static fields of `j`.
@@ -80,6 +89,29 @@ static int issue_sequence(const spp_batch_job* j, cudaStream_t st, const spp_dev
                                 j->ws.max_nodes, gst, job, 1))
       return bail(r);
     trace_mark(kTrGather, 0, gst);
+  } else if (j->feature_mode == 2 && j->do_split && tunables().gather_split != 0 && remote_class_mask(&j->fmap) != 0) {
+    // Rows of other GPUs' partitions are fetched by their own launch on a side stream, bucket by
+    // bucket (the owner split just built the buckets), while this stream gathers the rows that live
+    // in local HBM (hosted partitions + replicated cache): the NVLink-bound fetch and the HBM-bound
+    // gather overlap instead of sharing tiles.
+    const uint32_t peer_mask = remote_class_mask(&j->fmap);
+    const uint32_t local_mask = ((1u << (j->fmap.num_parts + 1)) - 1u) & ~peer_mask;
+    AuxStreams* ax = aux_streams(st);
+    if (!ax) return bail(fail(SPP_EINVAL, "spp_batch_enqueue: side stream missing"));
+    SPP_CUDA(cudaEventRecord(ax->fork_gather, st));
+    SPP_CUDA(cudaStreamWaitEvent(ax->gather, ax->fork_gather, 0));
+    int r = gather_by_class_job(&j->fmap, j->row_bytes, j->bucket_ids, j->split_scratch, j->ws.max_nodes, peer_mask, j->x_out,
+                                j->gather_counters, ax->gather, job);
+    trace_mark(kTrGather, 1, ax->gather);
+    // join unconditionally (a capture must not end with an un-joined stream)
+    cudaError_t je = cudaEventRecord(ax->join_gather, ax->gather);
+    if (r == 0)
+      r = gather_by_class_job(&j->fmap, j->row_bytes, j->bucket_ids, j->split_scratch, j->ws.max_nodes, local_mask, j->x_out,
+                              j->gather_counters, st, job);
+    trace_mark(kTrGather, 0, st);
+    if (je == cudaSuccess) je = cudaStreamWaitEvent(st, ax->join_gather, 0);
+    if (r) return bail(r);
+    SPP_CUDA(je);
   } else if (j->feature_mode == 2) {
     // the owner split (when it ran) left one source descriptor per node in its scratch: the gather
     // reads them sequentially instead of probing the cache index a second time
@@ -191,6 +223,7 @@ static int enqueue_replay(const spp_batch_job* j, cudaStream_t st, bool* done) {
     }
     if (int r = sorter_attributes()) return r;
     if (int r = gather_attributes()) return r;
+    aux_streams(st);  // side streams are created before the capture begins
     spp_batch_job cap;
     memcpy(&cap, j, sizeof(cap));
     cap.batch_size_cap = key.batch_size_cap;

@@ -44,6 +44,8 @@ class MiniBatchPipeline:
         self.feat_dim, self.feat_dtype = feat_dim, feat_dtype
         self.row_bytes = feat_dim * torch.empty(0, dtype=feat_dtype).element_size()
         self.split, self.use_cache = split, use_cache
+        import os
+        self.split_gather = os.environ.get("SPP_GATHER_SPLIT", "1") != "0"
         self.sz_arr = (ctypes.c_int32 * max(self.L, 1))(*self.sizes)
         self.caps = (ctypes.c_int64 * max(self.L, 1))(*[int(self.sz.hop_edges[h]) for h in range(self.L)])
         self.slots: List[_PipeSlot] = []
@@ -116,13 +118,30 @@ class MiniBatchPipeline:
                                             ctypes.c_uint64(rng_seed), ctypes.byref(s.ws.c), s.rp, s.cp, self.caps,
                                             None, s.stream.cuda_stream), "spp_sample_minibatch")
 
+    def remote_mask(self) -> int:
+        """Buckets (bit p: partition p) whose rows live on other GPUs (or are treated as such)."""
+        fm = self.fm
+        if fm is None:
+            return 0
+        local = (1 << fm.rank) | int(fm.local_parts)
+        return sum(1 << p for p in range(fm.num_parts) if not (local >> p) & 1 and fm.offsets[p + 1] > fm.offsets[p])
+
     def gather(self, s: _PipeSlot, count_rows: bool = False):
         n_dev = s.ws.meta_ptr(self.L)
-        if self.fm is not None:
+        cnt = s.counters.data_ptr() if count_rows else None
+        if self.fm is not None and self.split and self.remote_mask() and self.split_gather:
+            # what a batch does (session.cu): rows by source class, peer buckets and local buckets as
+            # two launches (here back to back on one stream so that CUDA events time both)
+            peer = self.remote_mask()
+            local = ((1 << (self.fm.num_parts + 1)) - 1) & ~peer
+            for mask in (peer, local):
+                check(self.lib.spp_gather_by_class(ctypes.byref(self.fm), self.row_bytes, s.bucket_ids.data_ptr(),
+                                                   s.scratch.data_ptr(), s.ws.max_nodes, mask, s.x.data_ptr(), cnt,
+                                                   s.stream.cuda_stream), "spp_gather_by_class")
+        elif self.fm is not None:
             check(self.lib.spp_gather_partitioned(ctypes.byref(self.fm), self.row_bytes, s.ws.n_ids.data_ptr(), 0,
                                                   s.ws.max_nodes, n_dev, s.scratch.data_ptr() if self.split else None,
-                                                  s.x.data_ptr(), s.ws.max_nodes,
-                                                  s.counters.data_ptr() if count_rows else None,
+                                                  s.x.data_ptr(), s.ws.max_nodes, cnt,
                                                   s.stream.cuda_stream), "spp_gather_partitioned")
         elif self.x_table is not None:
             check(self.lib.spp_gather_rows_pitched(self.x_table.ptr, self.x_table.pitch, self.row_bytes,

@@ -402,3 +402,60 @@ def test_session_batches_are_cuda_graph_replays(fs, data):
         assert n == 8
         assert int(L.spp_graph_replays()) - r0 == 8, "batches were not issued as graph launches"
         assert _lib.launch_count() - k0 >= 8 * 12          # kernels inside the graphs are accounted for
+
+
+@pytest.mark.parametrize("P,hosted", [(4, [1]), (8, [4, 5, 6, 7]), (2, [0])])
+@pytest.mark.parametrize("dim,dtype", [(128, torch.float16), (100, torch.float16), (7, torch.float32)])
+def test_gather_by_class_equals_fused_gather(fs, P, hosted, dim, dtype):
+    """spp_gather_by_class (rows of one set of buckets, walked in bucket order through the owner
+    split's inverse permutation): the peer launch + the local launch together write exactly what the
+    fused spp_gather_partitioned writes, i.e. x == f(n_id); counters add up class by class."""
+    from salient_plusplus_b200 import _lib
+    from salient_plusplus_b200.fast_sampler import make_feature_map
+    L = _lib.load()
+    N = 50000
+    X = S.features_by_id(0, N, dim, dtype, device="cuda") if dtype != torch.float32 or dim % 1 == 0 else None
+    off = S.equal_partition_offsets(N, P).tolist()
+    rank = hosted[0]
+    g = torch.Generator().manual_seed(P * 7 + dim)
+    n = 30011
+    n_id = torch.randperm(N, generator=g)[:n].cuda()
+    cv = torch.randperm(N, generator=g)[:6000]
+    own = torch.zeros(N, dtype=torch.bool)
+    for p in hosted:
+        own[off[p]:off[p + 1]] = True
+    cv = cv[~own[cv]]
+    cache = fs.Cache(rank, P, cv, X[cv.cuda()].contiguous())
+    ctab = cache.device_table()
+    tabs = [fs.feature_table(X[off[p]:off[p + 1]]) for p in range(P)]
+    fm = make_feature_map(off, rank, [t.storage for t in tabs], ctab.storage, cache.device_index(N), None, tabs[0].pitch,
+                          ctab.pitch, local_parts=hosted)
+    rb = dim * X.element_size()
+    sp = torch.cuda.current_stream().cuda_stream
+    scratch = torch.empty(int(L.spp_split_scratch_words(n)), dtype=torch.int32, device="cuda")
+    b_ids, b_perm = torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, dtype=torch.int64, device="cuda")
+    b_cnt = torch.zeros(P + 2, dtype=torch.int64, device="cuda")
+    _lib.check(L.spp_split_by_owner(ctypes.byref(fm), 1, n_id.data_ptr(), 1, n, None, b_ids.data_ptr(), b_perm.data_ptr(),
+                                    b_cnt.data_ptr(), scratch.data_ptr(), sp))
+    inv = scratch[n:2 * n]
+    assert torch.equal(b_perm[inv.long()], torch.arange(n, device="cuda"))        # inverse permutation
+    peer = sum(1 << p for p in range(P) if p not in hosted)
+    local = ((1 << (P + 1)) - 1) & ~peer
+    out = torch.zeros((n, dim), dtype=dtype, device="cuda")
+    c_peer, c_local = torch.zeros(3, dtype=torch.int64, device="cuda"), torch.zeros(3, dtype=torch.int64, device="cuda")
+    _lib.check(L.spp_gather_by_class(ctypes.byref(fm), rb, b_ids.data_ptr(), scratch.data_ptr(), n, peer, out.data_ptr(),
+                                     c_peer.data_ptr(), sp))
+    it = torch.int16 if X.element_size() == 2 else torch.int32
+    want = S._id_pattern(n_id, dim, dtype)
+    torch.cuda.synchronize()
+    part = torch.searchsorted(torch.tensor(off, device="cuda"), n_id, right=True) - 1
+    is_peer = ~own.cuda()[n_id] & ~torch.isin(n_id, cv.cuda())
+    got = out.view(it)
+    assert torch.equal(got[is_peer], want[is_peer]) and not bool(got[~is_peer].any())   # only peer rows written so far
+    _lib.check(L.spp_gather_by_class(ctypes.byref(fm), rb, b_ids.data_ptr(), scratch.data_ptr(), n, local, out.data_ptr(),
+                                     c_local.data_ptr(), sp))
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(it), want)
+    assert c_peer.tolist() == [0, 0, int(is_peer.sum())]
+    assert c_local.tolist() == [int(own.cuda()[n_id].sum()), int(torch.isin(n_id, cv.cuda()).sum()), 0]
+    assert int(part.max()) < P
