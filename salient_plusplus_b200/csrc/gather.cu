@@ -720,10 +720,9 @@ int gather_by_class_job(const spp_feature_map* m, int64_t row_bytes, const int64
       peers = peers || (m->tables[p] != nullptr && ipc_imported(m->tables[p]));
     }
   }
-  if ((class_mask >> m->num_parts) & 1u) {
-    if (!m->cache_table) return fail(SPP_EINVAL, "spp_gather_by_class: cached bucket without a cache table");
-    align |= (uintptr_t)m->cache_table | (uintptr_t)prm.cache_pitch;
-  }
+  if (((class_mask >> m->num_parts) & 1u) && !m->cache_table) class_mask &= ~(1u << m->num_parts);  // no cache: empty bucket
+  if ((class_mask >> m->num_parts) & 1u) align |= (uintptr_t)m->cache_table | (uintptr_t)prm.cache_pitch;
+  if (class_mask == 0) return 0;
   prm.cache_table = (const char*)m->cache_table;
   prm.counters = (unsigned long long*)counters;
   cp.bucket_ids = bucket_ids;
