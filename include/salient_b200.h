@@ -46,7 +46,7 @@ int spp_abi_version(void);
  *   "gather_ctas_per_sm" (0 = automatic), "gather_bulk" (-1 automatic, 0 never, 1 whenever the rows are
  *   multiples of 16 bytes: bulk-copy flavour of the gather), "bulk_tile" (bytes), "bulk_stages",
  *   "bulk_ctas_per_sm", "gather_split" (1: a batch's peer rows are fetched by their own launch on a
- *   side stream, see spp_gather_by_class; 0: one fused launch) */
+ *   side stream, see spp_gather_by_class; 0 (default): one fused launch), "gather_tile_rows" (0 automatic) */
 int spp_tune(const char* key, int value);
 const char* spp_last_error(void);
 /* number of kernels this library has launched in this process (bench.py `gpu_launches`) */

@@ -116,16 +116,18 @@ struct RowResolver {
   }
 };
 
-template <typename V, bool kPartitioned, typename IdxT>
+// ROWS = rows per tile (64: 16 KB of 256-byte rows in flight per CTA; 256 for maps with peer tables, whose
+// rows take an NVLink round trip: the tile must be deep enough to keep the link busy with 2 CTAs per SM)
+template <typename V, bool kPartitioned, typename IdxT, int ROWS>
 __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant__ GatherParams prm) {
-  __shared__ const char* s_src[2][kRows];
+  __shared__ const char* s_src[2][ROWS];
   const int tid = threadIdx.x;
   const GatherView gv = gather_view(prm);
   const int64_t n = gv.n;
-  const int64_t num_tiles = (n + kRows - 1) / kRows;
+  const int64_t num_tiles = (n + ROWS - 1) / ROWS;
   const IdxT* __restrict__ idx = reinterpret_cast<const IdxT*>(gv.idx);
   const uint32_t vpr = prm.vpr, magic = prm.vpr_magic;
-  const bool resolver = tid < kRows;  // warps 0 and 1
+  const bool resolver = tid < ROWS;  // warps 0 and 1
   unsigned long long cnt0 = 0, cnt1 = 0, cnt2 = 0;
   uint64_t pol = 0;
   if constexpr (kPartitioned) pol = l2_policy_evict_last();
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
   auto load_id = [&](int64_t tile, RowResolver<kPartitioned>& r) {
     r.on = false;
     if (tile < num_tiles) {
-      const int64_t row = tile * kRows + tid;
+      const int64_t row = tile * ROWS + tid;
       if (row < n) {
         r.id = (int64_t)idx[row];
         r.on = true;
@@ -166,16 +168,16 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
     RowResolver<kPartitioned> r0;
     load_id(tile, r0);
     load_id(tile + gridDim.x, r1);
-    r0.begin_lookup(prm, tile * kRows + tid, pol);
+    r0.begin_lookup(prm, tile * ROWS + tid, pol);
     publish(r0, 0);
   }
   __syncthreads();
   int buf = 0;
   for (; tile < num_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kRows;
-    const int rows = (int)((n - row0) < kRows ? (n - row0) : kRows);
+    const int64_t row0 = tile * ROWS;
+    const int rows = (int)((n - row0) < ROWS ? (n - row0) : ROWS);
     if (resolver) {
-      r1.begin_lookup(prm, (tile + gridDim.x) * kRows + tid, pol);  // tile t+1: id arrived a tile ago
+      r1.begin_lookup(prm, (tile + gridDim.x) * ROWS + tid, pol);  // tile t+1: id arrived a tile ago
       load_id(tile + 2 * (int64_t)gridDim.x, r2);  // tile t+2: id load in flight
     }
     const uint32_t chunks = (uint32_t)rows * vpr;
@@ -542,11 +544,6 @@ template <bool kPartitioned>
 static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaStream_t st) {
   if (prm.n_max <= 0) return 0;
   prm.vpr = (uint32_t)(prm.row_bytes / vec_bytes);
-  if ((uint64_t)prm.vpr * kRows >= (1ull << 31))
-    return fail(SPP_EUNSUPPORTED, "gather: row of %lld bytes too wide", (long long)prm.row_bytes);
-  const bool magic_ok = prm.vpr > 1 && (uint64_t)kRows * prm.vpr * prm.vpr < (1ull << 32);
-  prm.vpr_magic = magic_ok ? (uint32_t)(((1ull << 32) + prm.vpr - 1) / prm.vpr) : 0u;
-  const int64_t tiles = ceil_div(prm.n_max, kRows);
   // 4 CTAs / SM x 8 loads in flight per thread saturate HBM and leave half of every SM's thread
   // slots to the latency-bound sampler kernels of the other in-flight mini-batches.  When rows
   // come from peer GPUs the kernel is NVLink bound (~630 GB/s needs < 2 MB in flight) and holds
@@ -584,14 +581,30 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
     cps = 4;
     if (peers) cps = 2;
   }
+  // rows per tile: deeper tiles when rows may come over NVLink (latency ~3x HBM's), see k_gather
+  int tile_rows = tn.gather_tile_rows > 0 ? tn.gather_tile_rows : (peers ? 256 : 64);
+  tile_rows = tile_rows >= 256 ? 256 : tile_rows >= 128 ? 128 : 64;
+  if ((uint64_t)prm.vpr * tile_rows >= (1ull << 31))
+    return fail(SPP_EUNSUPPORTED, "gather: row of %lld bytes too wide", (long long)prm.row_bytes);
+  {
+    const bool mok = prm.vpr > 1 && (uint64_t)tile_rows * prm.vpr * prm.vpr < (1ull << 32);
+    prm.vpr_magic = mok ? (uint32_t)(((1ull << 32) + prm.vpr - 1) / prm.vpr) : 0u;
+  }
+  const int64_t tiles = ceil_div(prm.n_max, tile_rows);
   const int64_t max_ctas = (int64_t)num_sms() * cps;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
-#define SPP_GATHER_LAUNCH(V)                                                                    \
+#define SPP_GATHER_LAUNCH_R(V, R)                                                               \
   do {                                                                                          \
     if (idx_is_64)                                                                              \
-      k_gather<V, kPartitioned, int64_t><<<grid, kGatherThreads, 0, st>>>(prm);                 \
+      k_gather<V, kPartitioned, int64_t, R><<<grid, kGatherThreads, 0, st>>>(prm);              \
     else                                                                                        \
-      k_gather<V, kPartitioned, int32_t><<<grid, kGatherThreads, 0, st>>>(prm);                 \
+      k_gather<V, kPartitioned, int32_t, R><<<grid, kGatherThreads, 0, st>>>(prm);              \
+  } while (0)
+#define SPP_GATHER_LAUNCH(V)                                                                    \
+  do {                                                                                          \
+    if (tile_rows == 256) SPP_GATHER_LAUNCH_R(V, 256);                                          \
+    else if (tile_rows == 128) SPP_GATHER_LAUNCH_R(V, 128);                                     \
+    else SPP_GATHER_LAUNCH_R(V, 64);                                                            \
   } while (0)
   switch (vec_bytes) {
     case 16: SPP_GATHER_LAUNCH(int4); break;
@@ -601,6 +614,7 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
     default: SPP_GATHER_LAUNCH(char); break;
   }
 #undef SPP_GATHER_LAUNCH
+#undef SPP_GATHER_LAUNCH_R
   SPP_KERNEL_CHECK("k_gather");
   return 0;
 }

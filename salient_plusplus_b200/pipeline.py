@@ -45,7 +45,7 @@ class MiniBatchPipeline:
         self.row_bytes = feat_dim * torch.empty(0, dtype=feat_dtype).element_size()
         self.split, self.use_cache = split, use_cache
         import os
-        self.split_gather = os.environ.get("SPP_GATHER_SPLIT", "1") != "0"
+        self.split_gather = os.environ.get("SPP_GATHER_SPLIT", "0") != "0"
         self.sz_arr = (ctypes.c_int32 * max(self.L, 1))(*self.sizes)
         self.caps = (ctypes.c_int64 * max(self.L, 1))(*[int(self.sz.hop_edges[h]) for h in range(self.L)])
         self.slots: List[_PipeSlot] = []
