@@ -459,3 +459,36 @@ def test_gather_by_class_equals_fused_gather(fs, P, hosted, dim, dtype):
     assert c_peer.tolist() == [0, 0, int(is_peer.sum())]
     assert c_local.tolist() == [int(own.cuda()[n_id].sum()), int(torch.isin(n_id, cv.cuda()).sum()), 0]
     assert int(part.max()) < P
+
+
+@pytest.mark.parametrize("tile_rows", [64, 128, 256])
+@pytest.mark.parametrize("dim,dtype", [(128, torch.float16), (100, torch.float16), (768, torch.float16), (3, torch.float32)])
+def test_gather_tile_heights_are_bit_exact(fs, tile_rows, dim, dtype):
+    """k_gather with 64 / 128 / 256 rows per tile (the deep tiles are what a map with peer tables
+    uses): single table and partitioned, ragged counts."""
+    from salient_plusplus_b200 import _lib
+    from salient_plusplus_b200.fast_sampler import make_feature_map
+    L = _lib.load()
+    N, P, rank = 20000, 4, 2
+    X = S.features_by_id(0, N, dim, dtype, device="cuda")
+    tab = fs.feature_table(X)
+    off = S.equal_partition_offsets(N, P).tolist()
+    g = torch.Generator().manual_seed(dim * 3 + tile_rows)
+    rb = dim * X.element_size()
+    it = torch.int16 if X.element_size() == 2 else torch.int32
+    sp = torch.cuda.current_stream().cuda_stream
+    try:
+        _lib.tune("gather_tile_rows", tile_rows)
+        for n in (1, 63, 257, 5000, 12345):
+            ids = torch.randint(0, N, (n,), generator=g).cuda()
+            out = torch.zeros((n, dim), dtype=dtype, device="cuda")
+            _lib.check(L.spp_gather_rows_pitched(tab.ptr, tab.pitch, rb, ids.data_ptr(), 1, n, None, out.data_ptr(), n, sp))
+            assert torch.equal(out.view(it), S._id_pattern(ids, dim, dtype))
+            ptrs = [tab.ptr + off[p] * tab.pitch for p in range(P)]
+            fm = make_feature_map(off, rank, None, None, None, ptrs, tab.pitch, 0)
+            out.zero_()
+            _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), rb, ids.data_ptr(), 1, n, None, None, out.data_ptr(), n, None, sp))
+            torch.cuda.synchronize()
+            assert torch.equal(out.view(it), S._id_pattern(ids, dim, dtype))
+    finally:
+        _lib.tune("gather_tile_rows", 0)
