@@ -356,6 +356,10 @@ typedef struct spp_batch_job {
 
 /* issue every call of the job on the calling thread (asynchronous w.r.t. the GPU) */
 int spp_batch_enqueue(const spp_batch_job* job);
+/* graph replay only: capture, instantiate and upload the slot's graph now (set-up time) instead of
+ * with its first batch; needs the static fields of the job (the per-batch pointers may be dummies,
+ * only whether n_id_out / seeds_host are NULL matters).  No-op when job_dev is not set. */
+int spp_batch_prepare(const spp_batch_job* job);
 
 /* executor: one worker thread bound to `device`; jobs are issued in submission order */
 void* spp_executor_create(int device);

@@ -33,7 +33,7 @@ EXPORTED = [
     "spp_sampler_sizes", "spp_sample_minibatch", "spp_sample_begin", "spp_sample_hop_count",
     "spp_sample_hop_fill", "spp_sample_export_nids", "spp_debug_set_timeline",
     "spp_trace_begin", "spp_trace_end",
-    "spp_batch_enqueue", "spp_executor_create", "spp_executor_destroy", "spp_executor_submit",
+    "spp_batch_enqueue", "spp_batch_prepare", "spp_executor_create", "spp_executor_destroy", "spp_executor_submit",
     "spp_executor_poll", "spp_executor_wait", "spp_executor_times",
     "spp_vip_hop",
     "spp_ipc_export", "spp_ipc_import", "spp_ipc_close", "spp_enable_peer_access",
@@ -155,6 +155,7 @@ def load() -> ctypes.CDLL:
     L.spp_trace_end.restype = i64
     L.spp_trace_end.argtypes = [POINTER(i32), POINTER(i32), POINTER(c_uint64), POINTER(ctypes.c_double), i64]
     L.spp_batch_enqueue.argtypes = [POINTER(BatchJob)]
+    L.spp_batch_prepare.argtypes = [POINTER(BatchJob)]
     L.spp_executor_create.restype = vp
     L.spp_executor_create.argtypes = [ci]
     L.spp_executor_destroy.restype = None

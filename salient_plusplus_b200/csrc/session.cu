@@ -199,7 +199,8 @@ static void fill_device_job(const spp_batch_job* j, spp_device_job* d) {
   d->scan_epoch = next_scan_epoch();
 }
 
-static int enqueue_replay(const spp_batch_job* j, cudaStream_t st, bool* done) {
+// launch == false: only make sure the slot's graph exists (captured, instantiated, uploaded)
+static int enqueue_replay(const spp_batch_job* j, cudaStream_t st, bool* done, bool launch = true) {
   *done = false;
   spp_batch_job key;
   static_key(j, &key);
@@ -247,6 +248,12 @@ static int enqueue_replay(const spp_batch_job* j, cudaStream_t st, bool* done) {
     }
     memcpy(&e->key, &key, sizeof(key));
     e->kernels = kernels;
+    cudaGraphUpload(e->exec, st);  // the first launch does not pay for the upload
+    cudaGetLastError();
+  }
+  if (!launch) {
+    *done = true;
+    return 0;
   }
   fill_device_job(j, j->job_host);
   if (j->seeds_host && j->batch_size > 0) memcpy(j->seeds_stage_host, j->seeds_host, (size_t)j->batch_size * sizeof(int64_t));
@@ -259,13 +266,28 @@ static int enqueue_replay(const spp_batch_job* j, cudaStream_t st, bool* done) {
 
 }  // namespace spp
 
+static bool replay_eligible(const spp_batch_job* j) {
+  return j->job_dev && j->job_host && (!j->seeds_host || j->seeds_stage_host) && spp::graph_mode_enabled() &&
+         !spp::tracing_active() && spp::pipeline_flags() == 0;
+}
+
+// Capture + instantiate + upload the slot's graph ahead of its first batch (a Session does this at
+// set-up, so no mini-batch pays the ~1 ms of a capture).  Only the static part of the job matters.
+extern "C" int spp_batch_prepare(const spp_batch_job* j) {
+  using namespace spp;
+  if (!j) return fail(SPP_EINVAL, "spp_batch_prepare: null job");
+  if (j->n_hops < 0 || j->n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_batch_prepare: n_hops out of range");
+  if (!replay_eligible(j)) return 0;
+  bool done = false;
+  return enqueue_replay(j, (cudaStream_t)j->stream, &done, false);
+}
+
 extern "C" int spp_batch_enqueue(const spp_batch_job* j) {
   using namespace spp;
   if (!j) return fail(SPP_EINVAL, "spp_batch_enqueue: null job");
   cudaStream_t st = (cudaStream_t)j->stream;
   if (j->n_hops < 0 || j->n_hops > SPP_MAX_HOPS) return fail(SPP_EINVAL, "spp_batch_enqueue: n_hops out of range");
-  if (j->job_dev && j->job_host && (!j->seeds_host || j->seeds_stage_host) && graph_mode_enabled() && !tracing_active() &&
-      pipeline_flags() == 0) {
+  if (replay_eligible(j)) {
     bool done = false;
     if (int r = enqueue_replay(j, st, &done)) return r;
     if (done) return 0;

@@ -986,6 +986,12 @@ class Session:
                 j.fmap = self._fm
             else:
                 j.fmap = self._split_fm
+        # capture the slot's graph now (only the static fields matter; whether seeds are staged from
+        # the host and whether n_id is exported are part of them)
+        j.seeds_host = self._idx_host_ptr if self._idx_host is not None else None
+        j.n_id_out = slot.job_dev.data_ptr() if cfg.distributed else None   # placeholder, non-NULL
+        j.batch_size = j.batch_size_cap
+        check(self._lib.spp_batch_prepare(ctypes.byref(j)), "spp_batch_prepare")
 
     def _prime_allocator(self, slot: "_Slot", blocks: int = 3):
         """Per-batch outputs are allocated at their upper bounds from PyTorch's caching allocator

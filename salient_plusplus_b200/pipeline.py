@@ -110,6 +110,9 @@ class MiniBatchPipeline:
                 j.fmap = self.fm
             j.bucket_ids, j.perm = s.bucket_ids.data_ptr(), s.perm.data_ptr()
             j.bucket_counts, j.split_scratch = s.counts.data_ptr(), s.scratch.data_ptr()
+        if graph:
+            j.batch_size = self.bs
+            check(self.lib.spp_batch_prepare(ctypes.byref(j)), "spp_batch_prepare")
         return j
 
     # -- individual stages (all asynchronous on the slot's stream) ------------------------------
