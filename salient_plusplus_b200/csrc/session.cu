@@ -58,17 +58,8 @@ static int issue_sequence(const spp_batch_job* j, cudaStream_t st, const spp_dev
                                     j->n_id_out != nullptr))
     return r;
   const int64_t* n_dev = j->ws.meta + SPP_META_NODES(j->n_hops);
-  // optional: the feature + label gather on its own (lower-priority) stream
   cudaStream_t gst = st;
   AuxStreams* aux = nullptr;
-  if (!replay && (pipeline_flags() & 2) && (j->feature_mode || (j->y_table && bs > 0))) {
-    aux = aux_streams(st);
-    if (aux) {
-      SPP_CUDA(cudaEventRecord(aux->fork_gather, st));
-      SPP_CUDA(cudaStreamWaitEvent(aux->gather, aux->fork_gather, 0));
-      gst = aux->gather;
-    }
-  }
   // an error after the fork must still join the side stream back into `st` (otherwise work queued on
   // it would be left dangling behind the caller's synchronisation point)
   auto bail = [&](int r) {
@@ -83,6 +74,16 @@ static int issue_sequence(const spp_batch_job* j, cudaStream_t st, const spp_dev
                                    j->bucket_counts, j->split_scratch, st, job))
       return bail(r);
     trace_mark(kTrSplit, 0, st);
+  }
+  // optional (SPP_FORK bit 1): the feature + label gather on its own stream -- forked AFTER the owner
+  // split, whose source descriptors the gather reads
+  if (!replay && (pipeline_flags() & 2) && (j->feature_mode || (j->y_table && bs > 0))) {
+    aux = aux_streams(st);
+    if (aux) {
+      SPP_CUDA(cudaEventRecord(aux->fork_gather, st));
+      SPP_CUDA(cudaStreamWaitEvent(aux->gather, aux->fork_gather, 0));
+      gst = aux->gather;
+    }
   }
   if (j->feature_mode == 1) {
     if (int r = gather_rows_job(j->table, j->table_pitch, j->row_bytes, j->ws.n_ids, 0, j->ws.max_nodes, n_dev, j->x_out,

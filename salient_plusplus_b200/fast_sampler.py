@@ -932,7 +932,10 @@ class Session:
         for h in range(len(self._sizes)):
             T, E = int(sz.hop_targets[h]), max(int(sz.hop_edges[h]), 1)
             if h == 0 and edges0 is not None:
-                E = max(int(edges0), 1)
+                # rounded up so that the per-batch outputs fall into a handful of size classes the caching
+                # allocator can re-use (an exact size per batch made every few batches a cudaMalloc: ms)
+                E = min(max(-(-int(edges0) // 16384) * 16384, 16384), max(int(sz.hop_edges[h]), 1))
+                E = max(E, int(edges0), 1)
                 m = min(m, T + E)
             off.append((o, o + T + 1))
             o += T + 1 + E
