@@ -45,6 +45,8 @@ struct Tunables {
   int bulk_ctas_per_sm;    // SPP_BULK_CTAS_PER_SM
   int gather_split;        // SPP_GATHER_SPLIT         1: peer rows fetched by their own launch on a side stream
   int gather_tile_rows;    // SPP_GATHER_TILE_ROWS     0 = automatic (64; 256 when rows may come from peer GPUs)
+  int gather_l2_hint;      // SPP_GATHER_L2HINT        1: rows of a partitioned gather stream through L2 as evict_first
+                           //                          (keeps the evict_last cache index resident)
 };
 Tunables& tunables();
 
@@ -218,6 +220,35 @@ __device__ __forceinline__ uint32_t ld_l2hint(const uint32_t* p, uint64_t pol) {
   asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
   return r;
 }
+
+// streaming row loads / stores that are also marked evict_first in L2 (policy from l2_policy_evict_first)
+__device__ __forceinline__ int4 ld_stream(const int4* p, uint64_t pol) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int2 ld_stream(const int2* p, uint64_t pol) {
+  int2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int ld_stream(const int* p, uint64_t) { return ld_nc_na(p); }
+__device__ __forceinline__ short ld_stream(const short* p, uint64_t) { return ld_nc_na(p); }
+__device__ __forceinline__ char ld_stream(const char* p, uint64_t) { return ld_nc_na(p); }
+__device__ __forceinline__ void st_stream(int4* p, const int4& v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(int2* p, const int2& v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.s32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream(int* p, const int& v, uint64_t) { st_na(p, v); }
+__device__ __forceinline__ void st_stream(short* p, const short& v, uint64_t) { st_na(p, v); }
+__device__ __forceinline__ void st_stream(char* p, const char& v, uint64_t) { st_na(p, v); }
 
 // ---- cache index (replaces the reference's dense id -> cache-row arrays,
 //      fast_sampler/range_partition_book.cpp:152-158) ------------------------------------------

@@ -41,6 +41,7 @@ struct GatherParams {
   unsigned long long* counters;  // [3] local / cache / peer rows (optional)
   // graph replay: per-batch pointers come from the device job block (session.cu)
   const spp_device_job* job;
+  int l2_stream_hint;            // partitioned flavour: rows stream through L2 as evict_first
   int job_mode;                  // 1: out = job->x_out; 2 (labels): idx = job->seeds, out = job->y_out, n <= job->batch_size
 };
 
@@ -119,7 +120,7 @@ struct RowResolver {
 // ROWS = rows per tile (64: 16 KB of 256-byte rows in flight per CTA; 256 for maps with peer tables, whose
 // rows take an NVLink round trip: the tile must be deep enough to keep the link busy with 2 CTAs per SM)
 template <typename V, bool kPartitioned, typename IdxT, int ROWS>
-__global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant__ GatherParams prm) {
+__global__ void __launch_bounds__(kGatherThreads, 4) k_gather(const __grid_constant__ GatherParams prm) {
   __shared__ const char* s_src[2][ROWS];
   const int tid = threadIdx.x;
   const GatherView gv = gather_view(prm);
@@ -129,8 +130,13 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
   const uint32_t vpr = prm.vpr, magic = prm.vpr_magic;
   const bool resolver = tid < ROWS;  // warps 0 and 1
   unsigned long long cnt0 = 0, cnt1 = 0, cnt2 = 0;
-  uint64_t pol = 0;
-  if constexpr (kPartitioned) pol = l2_policy_evict_last();
+  uint64_t pol = 0, pol_stream = 0;
+  bool stream_hint = false;
+  if constexpr (kPartitioned) {
+    pol = l2_policy_evict_last();
+    stream_hint = prm.l2_stream_hint != 0;
+    if (stream_hint) pol_stream = l2_policy_evict_first();
+  }
 
   auto load_id = [&](int64_t tile, RowResolver<kPartitioned>& r) {
     r.on = false;
@@ -191,13 +197,17 @@ __global__ void __launch_bounds__(kGatherThreads) k_gather(const __grid_constant
         if (lc < chunks) {
           const uint32_t r = magic ? __umulhi(lc, magic) : lc / vpr;
           const uint32_t v = lc - r * vpr;
-          vals[u] = ld_nc_na(reinterpret_cast<const V*>(src[r]) + v);
+          const V* q = reinterpret_cast<const V*>(src[r]) + v;
+          vals[u] = stream_hint ? ld_stream(q, pol_stream) : ld_nc_na(q);
         }
       }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const uint32_t lc = base + u * kGatherThreads;
-        if (lc < chunks) st_na(dst + lc, vals[u]);
+        if (lc < chunks) {
+          if (stream_hint) st_stream(dst + lc, vals[u], pol_stream);
+          else st_na(dst + lc, vals[u]);
+        }
       }
     }
     if (resolver) {
@@ -691,6 +701,7 @@ int gather_partitioned_job(const spp_feature_map* m, int64_t row_bytes, const vo
   }
   prm.cache_table = (const char*)m->cache_table;
   prm.cache = make_cache_index(m->cache_index, m->cache_index_nodes);
+  prm.l2_stream_hint = (m->cache_index != nullptr && tunables().gather_l2_hint != 0) ? 1 : 0;
   prm.desc = src_desc;
   prm.book.local_mask = (1u << m->rank) | m->local_parts;
   align |= (uintptr_t)m->cache_table;

@@ -93,7 +93,7 @@ static int env_int(const char* name, int dflt) {
 Tunables& tunables() {
   static Tunables t = {env_int("SPP_GATHER_CTAS_PER_SM", 0), env_int("SPP_GATHER_BULK", -1), env_int("SPP_BULK_TILE", 4096),
                        env_int("SPP_BULK_STAGES", 6), env_int("SPP_BULK_CTAS_PER_SM", 2), env_int("SPP_GATHER_SPLIT", 0),
-                       env_int("SPP_GATHER_TILE_ROWS", 0)};
+                       env_int("SPP_GATHER_TILE_ROWS", 0), env_int("SPP_GATHER_L2HINT", 1)};
   return t;
 }
 
@@ -173,6 +173,7 @@ int spp_tune(const char* key, int value) {
   else if (!strcmp(key, "bulk_ctas_per_sm")) t.bulk_ctas_per_sm = value;
   else if (!strcmp(key, "gather_split")) t.gather_split = value;
   else if (!strcmp(key, "gather_tile_rows")) t.gather_tile_rows = value;
+  else if (!strcmp(key, "gather_l2_hint")) t.gather_l2_hint = value;
   else return spp::fail(SPP_EINVAL, "spp_tune: unknown key '%s'", key);
   return 0;
 }
