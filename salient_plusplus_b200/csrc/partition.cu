@@ -190,20 +190,35 @@ __global__ void __launch_bounds__(kSplitThreads) k_split_hist(const __grid_const
     if (threadIdx.x < kClasses) s_hist[threadIdx.x] = 0;
     __syncthreads();
     const int64_t base = tile * kSplitTile;
+    // phased so that the 8 rounds' loads are independent: ids -> index blocks -> rank2row -> histogram
+    // (one round at a time this kernel was bound by the latency of the two dependent probe loads)
+    int64_t nid[kSplitRounds];
+    int cls[kSplitRounds];
+    int32_t rank[kSplitRounds];
 #pragma unroll
     for (int r = 0; r < kSplitRounds; ++r) {
       const int64_t i = base + r * kSplitThreads + threadIdx.x;
-      if (i < n) {
-        const int64_t nid = (int64_t)ids[i];
-        int c = book_partid(prm.book, nid);
+      nid[r] = i < n ? (int64_t)ids[i] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < kSplitRounds; ++r) {
+      cls[r] = nid[r] >= 0 ? book_partid(prm.book, nid[r]) : -1;
+      rank[r] = -1;
+      // the ONE cache probe of this node: the scatter below and the fused gather read `desc`
+      if (cls[r] >= 0 && !book_is_local(prm.book, cls[r]) && prm.cache.nodes > 0) rank[r] = cache_rank(prm.cache, nid[r], pol);
+    }
+#pragma unroll
+    for (int r = 0; r < kSplitRounds; ++r)
+      if (rank[r] >= 0) rank[r] = (int32_t)ld_l2hint(reinterpret_cast<const uint32_t*>(prm.cache.rank2row) + rank[r], pol);
+#pragma unroll
+    for (int r = 0; r < kSplitRounds; ++r) {
+      const int64_t i = base + r * kSplitThreads + threadIdx.x;
+      if (cls[r] >= 0) {
+        int c = cls[r];
         int32_t d = c;
-        // the ONE cache probe of this node: the scatter below and the fused gather read `desc`
-        if (!book_is_local(prm.book, c) && prm.cache.nodes > 0) {
-          const int32_t row = cache_lookup(prm.cache, nid, pol);
-          if (row >= 0) {
-            c = P;
-            d = ~row;
-          }
+        if (rank[r] >= 0) {
+          c = P;
+          d = ~rank[r];
         }
         prm.desc[i] = d;
         atomicAdd(&s_hist[c], 1u);

@@ -93,7 +93,7 @@ static int env_int(const char* name, int dflt) {
 Tunables& tunables() {
   static Tunables t = {env_int("SPP_GATHER_CTAS_PER_SM", 0), env_int("SPP_GATHER_BULK", -1), env_int("SPP_BULK_TILE", 4096),
                        env_int("SPP_BULK_STAGES", 6), env_int("SPP_BULK_CTAS_PER_SM", 2), env_int("SPP_GATHER_SPLIT", 0),
-                       env_int("SPP_GATHER_TILE_ROWS", 0), env_int("SPP_GATHER_L2HINT", 1)};
+                       env_int("SPP_GATHER_TILE_ROWS", 0), env_int("SPP_GATHER_L2HINT", 0)};
   return t;
 }
 
