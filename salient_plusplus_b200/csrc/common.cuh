@@ -44,7 +44,7 @@ struct Tunables {
   int bulk_stages;         // SPP_BULK_STAGES
   int bulk_ctas_per_sm;    // SPP_BULK_CTAS_PER_SM
   int gather_split;        // SPP_GATHER_SPLIT         1: peer rows fetched by their own launch on a side stream
-  int gather_tile_rows;    // SPP_GATHER_TILE_ROWS     0 = automatic (64; 256 when rows may come from peer GPUs)
+  int gather_tile_rows;    // SPP_GATHER_TILE_ROWS     0 = automatic (64; 128 when rows may come from peer GPUs)
   int gather_l2_hint;      // SPP_GATHER_L2HINT        1: rows of a partitioned gather stream through L2 as evict_first
                            //                          (keeps the evict_last cache index resident)
 };
