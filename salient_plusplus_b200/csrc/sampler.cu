@@ -72,6 +72,32 @@ __device__ __forceinline__ uint32_t table_insert(const Table& t, int32_t key) {
   }
 }
 
+// insert-if-absent AND raise the entry's value to `val`, normally in ONE L2 atomic (every random
+// table access costs a 32-byte L2 sector whatever its width, and the sampler chain is bound by that
+// sector rate): direct-mapped tables take a 64-bit atomicMax on {val : key+1} (all writers of a slot
+// carry the same key, so the maximum is the maximum of val); hashed tables a 64-bit CAS on the
+// empty entry -- it either inserts {val : key+1}, or returns the resident entry, and only a resident
+// entry of the same key with a smaller value needs the second (32-bit) atomicMax.
+__device__ __forceinline__ uint32_t table_insert_max(const Table& t, int32_t key, uint32_t val) {
+  const uint32_t want = (uint32_t)key + 1u;
+  unsigned long long* tab64 = reinterpret_cast<unsigned long long*>(t.w);
+  const unsigned long long mine = ((unsigned long long)val << 32) | (unsigned long long)want;
+  uint32_t slot = table_home(t, key);
+  if (t.direct) {
+    atomicMax(tab64 + slot, mine);
+    return slot;
+  }
+  while (true) {
+    const unsigned long long old = atomicCAS(tab64 + slot, 0ull, mine);
+    if (old == 0ull) return slot;
+    if ((uint32_t)old == want) {
+      if ((uint32_t)(old >> 32) < val) atomicMax(t.w + 2 * (size_t)slot + 1, val);
+      return slot;
+    }
+    slot = (slot + 1) & t.mask;
+  }
+}
+
 __device__ __forceinline__ uint32_t table_find(const Table& t, int32_t key) {
   const uint32_t want = (uint32_t)key + 1u;
   uint32_t slot = table_home(t, key);
@@ -291,8 +317,7 @@ __device__ __forceinline__ int32_t load_col(const void* col, int64_t e) {
 }
 
 __device__ __forceinline__ void emit_candidate(const HopParams& prm, int64_t* out_col, int32_t node, uint32_t Tbase, int64_t p) {
-  const uint32_t slot = table_insert(prm.tab, node);
-  atomicMax(prm.tab.w + 2 * (size_t)slot + 1, ~(Tbase + (uint32_t)p));
+  const uint32_t slot = table_insert_max(prm.tab, node, ~(Tbase + (uint32_t)p));
   out_col[p] = (int64_t)slot;
 }
 
@@ -718,6 +743,11 @@ __global__ void k_export_nids(const spp_device_job* job, const int32_t* __restri
 //   C. k_relabel_sort_fused slot -> local id, register bitonic sort per row, compacted int64 row.
 // ================================================================================================
 constexpr uint32_t kInvalidCand = 0xFFFFFFFFu;
+// The compaction pass rewrites cand[v] to (local id | kResolvedCand) for every candidate whose local id
+// it already knows -- first discoverers (it assigns the id) and nodes of earlier hops (the entry holds
+// ~local with local < T) -- so the relabel pass only goes back to the table for the repeats of nodes
+// that are new in this hop (slots are < 2^31, local ids far below: the flag bit is free).
+constexpr uint32_t kResolvedCand = 0x80000000u;
 constexpr int kFusedItems = 8;
 constexpr int kFusedTile = kScanThreads * kFusedItems;  // 2048 virtual positions per tile
 
@@ -824,9 +854,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_hop_sample_fused(const __gri
     }
     // ---- stage C: insert the previous round's candidate ------------------------------------------
     if (c_valid) {
-      const uint32_t slot = table_insert(prm.tab, c_node);
-      atomicMax(prm.tab.w + 2 * (size_t)slot + 1, ~(Tbase + c_v));
-      fp.cand[c_v] = slot;
+      fp.cand[c_v] = table_insert_max(prm.tab, c_node, ~(Tbase + c_v));
     }
     if (!have) break;
     c_valid = b_valid;
@@ -966,12 +994,17 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
 #pragma unroll
     for (int q = 0; q < kFusedItems; ++q) {
       if (v0 + q < V) {
-        if (keptm & (1u << q)) ++kept_run;
+        if (keptm & (1u << q)) {
+          ++kept_run;
+          const uint32_t local = ~(uint32_t)(ent[q] >> 32);
+          if (local < Tbase) slot[q] = local | kResolvedCand;  // node of an earlier hop
+        }
         if (newm & (1u << q)) {
           const int64_t L = T + (int64_t)new_run;
           if (L < prm.max_nodes) {
             prm.n_ids[L] = (int32_t)((uint32_t)ent[q] - 1u);
             __stcg(prm.tab.w + 2 * (size_t)slot[q] + 1, ~(uint32_t)L);
+            slot[q] = (uint32_t)L | kResolvedCand;             // first discoverer: id assigned here
           }
           ++new_run;
         }
@@ -981,6 +1014,16 @@ __global__ void __launch_bounds__(kScanThreads) k_hop_compact_fused(const __grid
           ++row;
         }
       }
+    }
+    // candidates with their resolution back to cand (same 32-byte run this thread loaded)
+    if (v0 + kFusedItems <= V) {
+      uint4* cw = reinterpret_cast<uint4*>(fp.cand + v0);
+      cw[0] = make_uint4(slot[0], slot[1], slot[2], slot[3]);
+      cw[1] = make_uint4(slot[4], slot[5], slot[6], slot[7]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < kFusedItems; ++q)
+        if (v0 + q < V) fp.cand[v0 + q] = slot[q];
     }
     if (tile == num_tiles - 1 && threadIdx.x == 0) {
       const uint64_t kept_total = (base >> 32) + (total >> 16);
@@ -1023,8 +1066,8 @@ __global__ void __launch_bounds__(kSampleThreads) k_relabel_sort_fused(const __g
     }
     int32_t v = 0x7fffffff;
     if (gl < n) {
-      const uint32_t slot = fp.cand[i * k + gl];
-      v = (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)slot + 1);
+      const uint32_t c = fp.cand[i * k + gl];
+      v = (c & kResolvedCand) ? (int32_t)(c & ~kResolvedCand) : (int32_t)~__ldcg(prm.tab.w + 2 * (size_t)c + 1);
     }
     v = group_bitonic_sort<G>(v, gl);
     if (gl < n) o_col[p0 + gl] = (int64_t)v;
