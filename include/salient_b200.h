@@ -188,7 +188,7 @@ typedef struct spp_graph {
 /* Per-stream scratch of the sampler (caller allocates; sizes from spp_sampler_sizes). */
 typedef struct spp_sampler_ws {
   uint64_t* table;       /* hash table, table_slots entries of {key+1, ~local}                 */
-  int64_t table_slots;   /* power of two, >= 1.25 * max_nodes (spp_sampler_sizes gives >= 1.5x) */
+  int64_t table_slots;   /* >= 1.25 * max_nodes, any value (spp_sampler_sizes gives 1.35x)     */
   int32_t* n_ids;        /* int32[max_nodes]   global ids in first-discovery order             */
   int64_t max_nodes;
   int64_t* tgt_start;    /* int64[max_targets] rowptr[n] of each frontier node                  */

@@ -48,13 +48,12 @@ constexpr int kBlockSortSmemElems = 48 * 1024;  // int32 elements a CTA sorts in
 //                      trip per candidate, no probing (-7 % per mini-batch on the products shape).
 struct Table {
   uint32_t* w;  // interleaved {key+1, ~local}
-  int shift;    // 32 - log2(slots)
-  uint32_t mask;
+  uint32_t slots;  // hashed: any size >= 1.25 * node bound (multiply-high range reduction, no power of two needed)
   int direct;
 };
 
 __device__ __forceinline__ uint32_t table_home(const Table& t, int32_t key) {
-  return t.direct ? (uint32_t)key : ((uint32_t)key * 2654435761u) >> t.shift;
+  return t.direct ? (uint32_t)key : __umulhi((uint32_t)key * 2654435761u, t.slots);
 }
 
 // insert-if-absent; returns the slot of `key`
@@ -68,7 +67,7 @@ __device__ __forceinline__ uint32_t table_insert(const Table& t, int32_t key) {
   while (true) {  // optimistic: one L2 round trip when the slot is free or already holds the key
     const uint32_t prev = atomicCAS(t.w + 2 * (size_t)slot, 0u, want);
     if (prev == 0u || prev == want) return slot;
-    slot = (slot + 1) & t.mask;
+    slot = (slot + 1 == t.slots) ? 0u : slot + 1;
   }
 }
 
@@ -94,14 +93,14 @@ __device__ __forceinline__ uint32_t table_insert_max(const Table& t, int32_t key
       if ((uint32_t)(old >> 32) < val) atomicMax(t.w + 2 * (size_t)slot + 1, val);
       return slot;
     }
-    slot = (slot + 1) & t.mask;
+    slot = (slot + 1 == t.slots) ? 0u : slot + 1;
   }
 }
 
 __device__ __forceinline__ uint32_t table_find(const Table& t, int32_t key) {
   const uint32_t want = (uint32_t)key + 1u;
   uint32_t slot = table_home(t, key);
-  while (__ldcg(t.w + 2 * (size_t)slot) != want) slot = (slot + 1) & t.mask;
+  while (__ldcg(t.w + 2 * (size_t)slot) != want) slot = (slot + 1 == t.slots) ? 0u : slot + 1;
   return slot;
 }
 
@@ -1086,8 +1085,8 @@ static int check_ws(const spp_sampler_ws* ws) {
       return fail(SPP_EINVAL, "sampler: direct table needs 1 <= table_slots <= 2^31");
     return 0;  // table_slots >= num_nodes is checked where the graph is known
   }
-  if (ws->table_slots < 2 || (ws->table_slots & (ws->table_slots - 1)) || ws->table_slots > (1ll << 31))
-    return fail(SPP_EINVAL, "sampler: table_slots must be a power of two in [2, 2^31]");
+  if (ws->table_slots < 2 || ws->table_slots > (1ll << 31))
+    return fail(SPP_EINVAL, "sampler: table_slots must lie in [2, 2^31]");
   if (ws->table_slots * 4 < 5 * ws->max_nodes)
     return fail(SPP_ECAPACITY, "sampler: table_slots (%lld) < 1.25 * max_nodes (%lld)", (long long)ws->table_slots,
                 (long long)ws->max_nodes);
@@ -1097,10 +1096,7 @@ static int check_ws(const spp_sampler_ws* ws) {
 static Table make_table(const spp_sampler_ws* ws) {
   Table t;
   t.w = reinterpret_cast<uint32_t*>(ws->table);
-  int lg = 0;
-  while ((1ll << lg) < ws->table_slots) ++lg;
-  t.shift = 32 - lg;
-  t.mask = (uint32_t)(ws->table_slots - 1);
+  t.slots = (uint32_t)(ws->table_slots >= (1ll << 32) ? 0xFFFFFFFFll : ws->table_slots);
   t.direct = ws->table_direct != 0;
   return t;
 }
@@ -1494,13 +1490,19 @@ int spp_sampler_sizes(int64_t batch_size, const int32_t* sizes, int n_hops, int 
   for (int h = n_hops; h < SPP_MAX_HOPS; ++h) out->hop_targets[h] = out->hop_edges[h] = 0;
   out->max_nodes = T > 0 ? T : 1;
   out->max_targets = maxT > 0 ? maxT : 1;
-  int64_t slots = 1024;
-  while (2 * slots < 3 * out->max_nodes) slots <<= 1;  // load factor <= 2/3 at the node bound
-  if (slots > (1ll << 31)) return fail(SPP_EUNSUPPORTED, "spp_sampler_sizes: node bound %lld too large", (long long)T);
+  int64_t pow2 = 1024;
+  while (2 * pow2 < 3 * out->max_nodes) pow2 <<= 1;  // round 1's table size: still the yardstick for "direct or hashed"
+  if (pow2 > (1ll << 31)) return fail(SPP_EUNSUPPORTED, "spp_sampler_sizes: node bound %lld too large", (long long)T);
+  // hashed table: 1.35 x the node bound, rounded up to 1024 slots (any size works: the home slot is a
+  // multiply-high range reduction).  Load factor <= 0.74 at the bound, ~0.3 for typical batches; a third
+  // less to clear per batch and to keep L2 resident than the next power of two (11.7 vs 16.8 MB at
+  // (15,10,5) @ 1024).
+  int64_t slots = ((out->max_nodes * 27 + 19) / 20 + 1023) & ~1023ll;
+  if (slots < 1024) slots = 1024;
   out->table_slots = slots;
   out->table_direct = 0;
   const char* force = getenv("SPP_TABLE");  // "hash" / "direct": override the choice (tests, experiments)
-  const bool want_direct = force && force[0] == 'd' ? true : force && force[0] == 'h' ? false : 2 * num_nodes <= 3 * slots;
+  const bool want_direct = force && force[0] == 'd' ? true : force && force[0] == 'h' ? false : 2 * num_nodes <= 3 * pow2;
   if (num_nodes > 0 && num_nodes <= (1ll << 31) && want_direct) {  // direct map no bigger than 1.5x the hash table
     out->table_direct = 1;
     out->table_slots = num_nodes;

@@ -49,13 +49,13 @@ def test_sampler_sizes_host_only(lib):
     assert list(out.hop_targets)[:3] == [1024, 16384, 180224]
     assert list(out.hop_edges)[:3] == [15360, 163840, 901120]
     assert out.max_nodes == 1081344 and out.max_targets == 180224
-    assert out.table_slots == 2097152 and out.cand_words == 15360 + 163840 + 901120 + 16  # one range per hop
+    assert out.table_slots == 1460224 and out.cand_words == 15360 + 163840 + 901120 + 16  # one range per hop
     # node bound capped by the graph size, edge bound by the maximum degree
     assert lib.spp_sampler_sizes(1024, sizes, 3, 0, 100000, 7, ctypes.byref(out)) == 0
     assert out.max_nodes == 101024 and list(out.hop_edges)[:3] == [1024 * 7, 8192 * 7, 65536 * 5]
     assert out.table_direct == 1 and out.table_slots == 100000      # small graph: direct-mapped table
     assert lib.spp_sampler_sizes(1024, sizes, 3, 0, 111059956, 500, ctypes.byref(out)) == 0
-    assert out.table_direct == 0 and out.table_slots == 2097152     # papers100M-sized graph: hashed, L2 resident
+    assert out.table_direct == 0 and out.table_slots == 1460224     # papers100M-sized graph: hashed (1.35 x node bound), L2 resident
     # with replacement every target with a neighbour emits exactly k edges: no max_degree tightening
     assert lib.spp_sampler_sizes(1024, sizes, 3, 1, 100000, 7, ctypes.byref(out)) == 0
     assert list(out.hop_edges)[:2] == [15360, 163840]
