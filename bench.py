@@ -327,9 +327,9 @@ def reference_arm(args):
         x = S.features_by_id(0, n, f, dt, device=dev).cpu()
         y = S.labels_by_id(torch.arange(n))
         preroll = 2 * threads
-        # a reference "step" is a bundle of m mini-batches so that the K timed steps cover >= 10 waves of
+        # a reference "step" is a bundle of m mini-batches so that the K timed steps cover >= 20 waves of
         # the thread pool (20 single batches on 16-32 threads are ~1 wave: a +-2.7x error)
-        m = max(1, -(-10 * threads // max(K, 1)))
+        m = max(1, -(-20 * threads // max(K, 1)))
         need = (preroll + W + K * m) * bs
         if layerwise:
             idx = torch.arange(n, dtype=torch.int64)[:min(n, need)]
@@ -354,7 +354,7 @@ def reference_arm(args):
         off = S.equal_partition_offsets(n, P)
         threads_each = max(1, threads // N)
         preroll = 2 * threads_each
-        m = max(1, -(-10 * threads_each // max(K, 1)))   # batches per step and Session (>= 10 waves timed)
+        m = max(1, -(-20 * threads_each // max(K, 1)))   # batches per step and Session (>= 20 waves timed)
         need = (preroll + W + K * m + 4) * bs
         y = S.labels_by_id(torch.arange(n))
         x_blocks, idxs, caches, part_ranks = [], [], [], []

@@ -400,3 +400,26 @@ def test_device_side_epoch_shuffle_feeds_a_session_without_host_seeds(fs, data):
                                      rng_seed=O.session_rng_seed(en))
         assert adjs_equal(adjs, oa) and torch.equal(xb.cpu(), x[torch.from_numpy(on)]) and torch.equal(yb.cpu(), y[idx_h[st:en]])
     assert sess.blocking_get_batch() is None
+
+
+def test_plain_launches_match_graph_replay():
+    """SPP_GRAPH=0 (every kernel launched on the stream, read once per process by the library) and
+    the default graph replay produce the same batches: the Session tests are re-run in a child
+    process with replay switched off (the parent process ran them with replay on)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPP_GRAPH="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_session.py"), "-q", "-x",
+                        "-m", "gpu", "-k", "test_session_nondistributed or test_session_distributed_single_process"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+def test_tunables_reject_unknown_keys():
+    from salient_plusplus_b200 import _lib
+    with pytest.raises(_lib.SalientB200Error):
+        _lib.tune("no_such_switch", 1)
+    _lib.tune("gather_tile_rows", 0)
