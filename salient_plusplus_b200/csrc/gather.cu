@@ -556,10 +556,9 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
   prm.vpr = (uint32_t)(prm.row_bytes / vec_bytes);
   // 4 CTAs / SM x 8 loads in flight per thread saturate HBM and leave half of every SM's thread
   // slots to the latency-bound sampler kernels of the other in-flight mini-batches.  When rows
-  // come from peer GPUs the kernel is NVLink bound (~630 GB/s needs < 2 MB in flight) and holds
-  // its CTAs 3-5x longer: 2 CTAs / SM keep the link just as busy and leave the sampler kernels of
-  // the other in-flight batches three quarters of every SM (+2.6 % at 2 GPUs, +6.6 % at 4 on the
-  // products shape, profiles/r01_ab_multi_gather_ctas.txt)
+  // come from peer GPUs the kernel is NVLink bound and holds its CTAs 3-5x longer, and several
+  // batches' gathers are resident at once: ONE CTA per SM with a 128-row tile (32 KB of rows in
+  // flight per SM and gather) keeps the link as busy and leaves the SMs to the samplers.
   const Tunables& tn = tunables();
   int cps = tn.gather_ctas_per_sm > 0 ? tn.gather_ctas_per_sm : 0;
   bool peers = false;
@@ -589,7 +588,8 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
   }
   if (cps == 0) {
     cps = 4;
-    if (peers) cps = 2;
+    if (peers) cps = 1;  // round 2, with 128-row tiles: 1 / 2 CTAs per SM = 93.1 / 96.7 us per batch at 2 GPUs,
+                         // 121.4 / 130.9 at 4 (profiles/r02_ab_nvlink_regime_g*.txt)
   }
   // rows per tile: deeper tiles when rows may come over NVLink (latency ~3x HBM's), see k_gather
   // (128: at 2 GPUs as fast as 256, and with ~460 k rows over 296 persistent CTAs the last round of
