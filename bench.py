@@ -945,8 +945,13 @@ def layerwise(args):
         pass
     barrier()
     launches0 = lib.spp_launch_count()
+    caps0, mem0 = int(lib.spp_graph_captures()), torch.cuda.memory_stats()
     # value: seeds resident in HBM (the Session uses a device idx in place: no H2D)
-    _, ms, nodes_v, edges_v, _, _, _ = timed_loop(idx)
+    _, ms, nodes_v, edges_v, lat_v, _, _ = timed_loop(idx)
+    mem1 = torch.cuda.memory_stats()
+    diag = {"graph_captures_in_timed_loop": int(lib.spp_graph_captures()) - caps0,
+            "device_allocs_in_timed_loop": int(mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0)),
+            "slowest_batch_us": round(max(lat_v) * 1e6, 1) if lat_v else None}
     launches = int(lib.spp_launch_count() - launches0) * K // (W + K)
     barrier()
     # per-kernel time of the dominant kernel: event trace of a few batches at depth 1
@@ -1045,6 +1050,7 @@ def layerwise(args):
                                      "max": round(lat[-1] * 1e6, 1), "first_batch_after_iter_creation": round(first_us, 1)}},
             "gpu_launches": launches, "clocks": clk,
             "kernel_ms": {k_: round(v, 5) for k_, v in sorted(k_ms.items())},
+            "value_loop_diagnostics": diag,
             "roofline": {"bound": "hbm", "kernel": "k_hop_sample_edges (edge-parallel full-neighbourhood sampling + id-table insert)",
                          "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
                          "peak_source": peak_src, "avg_launch_ms": round(s_ms, 5), "algorithmic_bytes_per_launch": int(alg),

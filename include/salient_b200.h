@@ -53,6 +53,9 @@ const char* spp_last_error(void);
 uint64_t spp_launch_count(void);
 /* number of mini-batches issued as ONE CUDA-graph launch (spp_batch_job.job_dev set; SPP_GRAPH=0 disables) */
 uint64_t spp_graph_replays(void);
+/* number of graph captures so far (one per slot and job shape; a growing count during steady state
+ * means jobs keep changing their static part) */
+uint64_t spp_graph_captures(void);
 
 /* ------------------------------------------------------------------------------------------
  * K4 -- feature gather.  Replaces serial_index (fast_sampler/fast_sampler.cpp:238-279) and,

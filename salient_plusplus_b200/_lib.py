@@ -25,7 +25,7 @@ META_EDGES0 = 12
 META_OVERFLOW = 24
 
 EXPORTED = [
-    "spp_abi_version", "spp_tune", "spp_last_error", "spp_launch_count", "spp_graph_replays",
+    "spp_abi_version", "spp_tune", "spp_last_error", "spp_launch_count", "spp_graph_replays", "spp_graph_captures",
     "spp_gather_rows", "spp_gather_rows_pitched", "spp_gather_partitioned", "spp_gather_by_class",
     "spp_nid2partid", "spp_nid2localnid", "spp_nid_is_local",
     "spp_cache_index_bytes", "spp_cache_build_index", "spp_nid_is_cached", "spp_nid2cachenid",
@@ -125,6 +125,7 @@ def load() -> ctypes.CDLL:
     L.spp_tune.argtypes = [c_char_p, ci]
     L.spp_launch_count.restype = c_uint64
     L.spp_graph_replays.restype = c_uint64
+    L.spp_graph_captures.restype = c_uint64
     L.spp_gather_rows.argtypes = [vp, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_rows_pitched.argtypes = [vp, i64, i64, vp, ci, i64, vp, vp, i64, vp]
     L.spp_gather_partitioned.argtypes = [POINTER(FeatureMap), i64, vp, ci, i64, vp, vp, vp, i64, vp, vp]

@@ -13,6 +13,7 @@ int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 void count_replay();
+void count_capture();
 int num_sms();
 
 // diagnostics (runtime.cu): event mark on `st` after an operation was issued; no-op unless a

@@ -31,6 +31,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 void count_launch(int n) { g_launches.fetch_add((uint64_t)(int64_t)n, std::memory_order_relaxed); }
 static std::atomic<uint64_t> g_replays{0};
 void count_replay() { g_replays.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<uint64_t> g_captures{0};
+void count_capture() { g_captures.fetch_add(1, std::memory_order_relaxed); }
 bool tracing_active() { return g_trace_on.load(std::memory_order_relaxed) != 0; }
 
 int num_sms() {
@@ -182,6 +184,7 @@ int spp_abi_version(void) { return SPP_ABI_VERSION; }
 const char* spp_last_error(void) { return spp::g_err; }
 uint64_t spp_launch_count(void) { return spp::g_launches.load(std::memory_order_relaxed); }
 uint64_t spp_graph_replays(void) { return spp::g_replays.load(std::memory_order_relaxed); }
+uint64_t spp_graph_captures(void) { return spp::g_captures.load(std::memory_order_relaxed); }
 
 // ---- CUDA IPC ---------------------------------------------------------------------------------
 // The feature partition of every rank is exported once at set-up; peers map it and the gather

@@ -249,6 +249,7 @@ static int enqueue_replay(const spp_batch_job* j, cudaStream_t st, bool* done, b
     }
     memcpy(&e->key, &key, sizeof(key));
     e->kernels = kernels;
+    count_capture();
     cudaGraphUpload(e->exec, st);  // the first launch does not pay for the upload
     cudaGetLastError();
   }
