@@ -1001,8 +1001,6 @@ class Session:
         on the slot's stream.  A cache miss there is a cudaMalloc of a few hundred MB (2-30 ms,
         measured), so the first time a slot sees a given output size its pool is primed with the
         blocks a steady-state pipeline needs (in flight + held by the consumer + prefetched)."""
-        if self._batch_edges is not None:
-            return  # outputs are sized batch by batch
         fdim, fdtype = self._feat_shape
         x_rows = slot.ws.max_nodes if slot.cjob.feature_mode else 0
         key = (self._lay[3], x_rows, fdim, fdtype)
@@ -1023,7 +1021,11 @@ class Session:
     def _enqueue(self):
         slot = self._free.popleft()
         start, stop = self._ranges[self._next]
-        lay = self._lay if self._batch_edges is None else self._layout(self._batch_edges[self._next])
+        # layer-wise batches too are allocated at the Session-wide bound (the edge count of the largest
+        # batch): sizing them batch by batch made the caching allocator fall through to cudaMalloc /
+        # cudaFree in steady state (stalls of 3-80 ms); the exact per-batch capacity still travels to
+        # the kernels (out_col_cap) and the views are cut to the exact sizes
+        lay = self._lay
         self._next += 1
         bs = stop - start
         cfg = self._config
