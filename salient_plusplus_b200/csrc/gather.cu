@@ -41,6 +41,7 @@ struct GatherParams {
   unsigned long long* counters;  // [3] local / cache / peer rows (optional)
   // graph replay: per-batch pointers come from the device job block (session.cu)
   const spp_device_job* job;
+  int src_align16;               // every source base and pitch is a multiple of 16 bytes (bulk-copy eligibility)
   int l2_stream_hint;            // partitioned flavour: rows stream through L2 as evict_first
   int job_mode;                  // 1: out = job->x_out; 2 (labels): idx = job->seeds, out = job->y_out, n <= job->batch_size
 };
@@ -285,7 +286,13 @@ __global__ void __launch_bounds__(kBulkWarps * 32) k_gather_bulk(const __grid_co
   const GatherView gv = gather_view(prm);
   const int64_t n = gv.n;
   const uint32_t row_bytes = (uint32_t)prm.row_bytes;
-  const uint32_t stage_bytes = (uint32_t)tile_rows * row_bytes;
+  // Rows whose size is not a multiple of 16 bytes (ogbn-products: 200 bytes in a 256-byte pitch) are
+  // copied as round_up(row_bytes, 16) bytes -- the pitch guarantees the tail is readable -- into a
+  // shared-memory tile of that stride, and the warp then stores the dense rows itself (8- or 4-byte
+  // words); multiples of 16 leave as one bulk store per tile.
+  const uint32_t copy_bytes = (row_bytes + 15u) & ~15u;
+  const bool dense = copy_bytes == row_bytes;
+  const uint32_t stage_bytes = (uint32_t)tile_rows * copy_bytes;
   unsigned char* my = s_raw + (size_t)warp * stages * stage_bytes;
   uint64_t* bar = s_bar[warp];
   if (lane == 0) {
@@ -316,12 +323,12 @@ __global__ void __launch_bounds__(kBulkWarps * 32) k_gather_bulk(const __grid_co
   auto issue = [&](int64_t tile, int stage, RowResolver<kPartitioned>& r) {
     const int64_t row0 = tile * tile_rows;
     const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
-    if (lane == 0) mbar_expect_tx(bar + stage, (uint32_t)rows * row_bytes);
+    if (lane == 0) mbar_expect_tx(bar + stage, (uint32_t)rows * copy_bytes);
     __syncwarp();
     r.begin_lookup(prm, row0 + lane, pol);
     int cls;
     const char* src = r.finish(prm, cls);
-    if (r.on) bulk_g2s(my + (size_t)stage * stage_bytes + (size_t)lane * row_bytes, src, row_bytes, bar + stage);
+    if (r.on) bulk_g2s(my + (size_t)stage * stage_bytes + (size_t)lane * copy_bytes, src, copy_bytes, bar + stage);
     if constexpr (kPartitioned) {
       if (prm.counters != nullptr) {
         const uint32_t m0 = __ballot_sync(kFullMask, cls == 0), m1 = __ballot_sync(kFullMask, cls == 1),
@@ -349,15 +356,40 @@ __global__ void __launch_bounds__(kBulkWarps * 32) k_gather_bulk(const __grid_co
   uint32_t parity = 0;
   for (int64_t tile = wglobal; tile < num_tiles; tile += wstride, ++k) {
     mbar_wait(bar + stage, parity);
-    if (lane == 0) {
+    {
       const int64_t row0 = tile * tile_rows;
       const int rows = (int)((n - row0) < tile_rows ? (n - row0) : tile_rows);
-      bulk_s2g(gv.out + row0 * prm.row_bytes, my + (size_t)stage * stage_bytes, (uint32_t)rows * row_bytes);
-      bulk_commit();
+      if (dense) {
+        if (lane == 0) {
+          bulk_s2g(gv.out + row0 * prm.row_bytes, my + (size_t)stage * stage_bytes, (uint32_t)rows * row_bytes);
+          bulk_commit();
+        }
+      } else {
+        const unsigned char* tile_s = my + (size_t)stage * stage_bytes;
+        char* tile_g = gv.out + row0 * prm.row_bytes;
+        if ((row_bytes & 7u) == 0u && ((uintptr_t)gv.out & 7u) == 0u) {
+          const uint32_t wpr = row_bytes >> 3, words = (uint32_t)rows * wpr;
+          for (uint32_t e = lane; e < words; e += 32) {
+            const uint32_t rr = e / wpr, o = e - rr * wpr;
+            const int2 v = *reinterpret_cast<const int2*>(tile_s + (size_t)rr * copy_bytes + ((size_t)o << 3));
+            st_na(reinterpret_cast<int2*>(tile_g) + e, v);
+          }
+        } else {
+          const uint32_t wpr = row_bytes >> 2, words = (uint32_t)rows * wpr;
+          for (uint32_t e = lane; e < words; e += 32) {
+            const uint32_t rr = e / wpr, o = e - rr * wpr;
+            const int v = *reinterpret_cast<const int*>(tile_s + (size_t)rr * copy_bytes + ((size_t)o << 2));
+            st_na(reinterpret_cast<int*>(tile_g) + e, v);
+          }
+        }
+        // generic-proxy reads of the stage are ordered before the async-proxy writes that refill it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+      }
     }
     if (t_issue < num_tiles) {
       // the next load goes into the stage of tile k - 2: its store (two commits ago) must have finished reading
-      if (lane == 0) bulk_wait_read<2>();
+      if (lane == 0 && dense) bulk_wait_read<2>();
       __syncwarp();
       RowResolver<kPartitioned> cur = nxt;
       load_row(t_issue + wstride, nxt);
@@ -564,16 +596,20 @@ static int launch_gather(GatherParams& prm, int vec_bytes, int idx_is_64, cudaSt
   bool peers = false;
   if constexpr (kPartitioned) peers = map_has_peer_tables(prm);
   const int bulk_mode = tn.gather_bulk;
-  if (vec_bytes == 16 && prm.row_bytes <= 8192 && (bulk_mode == 1 || (bulk_mode < 0 && peers && bulk_default_for_peers()))) {
+  const int64_t copy_bytes = (prm.row_bytes + 15) & ~15ll;
+  const bool bulk_ok = prm.row_bytes <= 8192 && (vec_bytes == 16 || (prm.src_align16 && (prm.row_bytes & 3) == 0 &&
+                                                                       copy_bytes <= prm.table_pitch &&
+                                                                       (!kPartitioned || prm.cache_table == nullptr || copy_bytes <= prm.cache_pitch)));
+  if (bulk_ok && (bulk_mode == 1 || (bulk_mode < 0 && peers && bulk_default_for_peers()))) {
     const int tile_bytes = tn.bulk_tile > 0 ? tn.bulk_tile : 4096;
     int stages = tn.bulk_stages;
     if (stages < 3) stages = 3;
     if (stages > kBulkMaxStages) stages = kBulkMaxStages;
     const int bcps = tn.bulk_ctas_per_sm > 0 ? tn.bulk_ctas_per_sm : 2;
-    int tile_rows = (int)(tile_bytes / prm.row_bytes);
+    int tile_rows = (int)(tile_bytes / copy_bytes);
     if (tile_rows > 32) tile_rows = 32;
     if (tile_rows < 1) tile_rows = 1;
-    const size_t smem = (size_t)kBulkWarps * stages * tile_rows * prm.row_bytes;
+    const size_t smem = (size_t)kBulkWarps * stages * tile_rows * copy_bytes;
     if (smem <= 200 * 1024) {
       if (int r = gather_attributes()) return r;
       const int64_t btiles = ceil_div(prm.n_max, tile_rows);
@@ -659,6 +695,7 @@ int gather_rows_job(const void* table, int64_t table_pitch, int64_t row_bytes, c
   prm.table_pitch = table_pitch;
   prm.job = job;
   prm.job_mode = job ? job_mode : 0;
+  prm.src_align16 = ((((uintptr_t)table | (uintptr_t)table_pitch) & 15u) == 0u) ? 1 : 0;
   // with a job block the output address is not known to the host: torch allocations (512-byte
   // aligned) are assumed; rows that need a narrower vector because of their size still get it
   int vb = pick_vec_bytes(row_bytes, (uintptr_t)table | (job ? 0 : (uintptr_t)out) | (uintptr_t)table_pitch);
@@ -702,6 +739,11 @@ int gather_partitioned_job(const spp_feature_map* m, int64_t row_bytes, const vo
     align |= (uintptr_t)m->tables[p];
   }
   prm.cache_table = (const char*)m->cache_table;
+  {
+    uintptr_t sa = (uintptr_t)prm.table_pitch | (uintptr_t)m->cache_table | (m->cache_table ? (uintptr_t)prm.cache_pitch : 0);
+    for (int p = 0; p < m->num_parts; ++p) sa |= (uintptr_t)m->tables[p];
+    prm.src_align16 = (sa & 15u) == 0u ? 1 : 0;
+  }
   prm.cache = make_cache_index(m->cache_index, m->cache_index_nodes);
   prm.l2_stream_hint = (m->cache_index != nullptr && tunables().gather_l2_hint != 0) ? 1 : 0;
   prm.desc = src_desc;

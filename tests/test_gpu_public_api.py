@@ -316,6 +316,50 @@ def test_async_slice_tensors_against_compiled_reference(fs, data):
         assert torch.equal(g_[1].cpu(), w_[1]) and torch.equal(g_[2].cpu(), w_[2]), f"positions of request {i}"
 
 
+@pytest.mark.parametrize("dim,dtype", [(100, torch.float16), (50, torch.float32), (37, torch.float16)])
+@pytest.mark.parametrize("tile,stages", [(4096, 6), (1024, 4)])
+def test_bulk_copy_gather_of_pitched_rows(fs, dim, dtype, tile, stages):
+    """Rows that are not multiples of 16 bytes in a 128-byte-multiple pitch (ogbn-products: 200 bytes
+    in 256): the bulk flavour copies round_up(row, 16) bytes per row into shared memory and the warp
+    stores the dense rows (8- or 4-byte words; 74-byte rows are not eligible and take the LDG path)."""
+    from salient_plusplus_b200 import _lib
+    from salient_plusplus_b200.fast_sampler import make_feature_map
+    L = _lib.load()
+    N, P, rank = 30000, 4, 3
+    X = S.features_by_id(0, N, dim, dtype, device="cuda")
+    tab = fs.feature_table(X)
+    rb = dim * X.element_size()
+    assert tab.pitch % 128 == 0 and tab.pitch > rb
+    off = S.equal_partition_offsets(N, P).tolist()
+    it = torch.int16 if X.element_size() == 2 else torch.int32
+    g = torch.Generator().manual_seed(dim)
+    sp = torch.cuda.current_stream().cuda_stream
+    try:
+        for k_, v_ in (("gather_bulk", 1), ("bulk_tile", tile), ("bulk_stages", stages)):
+            _lib.tune(k_, v_)
+        for n in (1, 19, 20, 4097, 25013):
+            ids = torch.randint(0, N, (n,), generator=g).cuda()
+            out = torch.zeros((n + 1, dim), dtype=dtype, device="cuda")
+            _lib.check(L.spp_gather_rows_pitched(tab.ptr, tab.pitch, rb, ids.data_ptr(), 1, n, None, out.data_ptr(), n, sp))
+            assert torch.equal(out[:n].view(it), S._id_pattern(ids, dim, dtype)) and not bool(out[n:].any())
+            cv = torch.randperm(N, generator=g)[:4000]
+            cv = cv[(cv < off[rank]) | (cv >= off[rank + 1])]
+            cache = fs.Cache(rank, P, cv, X[cv.cuda()].contiguous())
+            ctab = cache.device_table()
+            ptrs = [tab.ptr + off[p] * tab.pitch for p in range(P)]
+            fm = make_feature_map(off, rank, None, ctab.storage, cache.device_index(N), ptrs, tab.pitch, ctab.pitch)
+            out.zero_()
+            cnt = torch.zeros(3, dtype=torch.int64, device="cuda")
+            _lib.check(L.spp_gather_partitioned(ctypes.byref(fm), rb, ids.data_ptr(), 1, n, None, None, out.data_ptr(), n,
+                                                cnt.data_ptr(), sp))
+            torch.cuda.synchronize()
+            assert torch.equal(out[:n].view(it), S._id_pattern(ids, dim, dtype)) and int(cnt.sum()) == n
+            assert int(cnt[1]) == int(torch.isin(ids.cpu(), cv).sum())
+    finally:
+        for k_, v_ in (("gather_bulk", -1), ("bulk_tile", 4096), ("bulk_stages", 6)):
+            _lib.tune(k_, v_)
+
+
 @pytest.mark.parametrize("dim,dtype", [(128, torch.float16), (768, torch.float16), (128, torch.float32), (8, torch.float16)])
 @pytest.mark.parametrize("tile,stages", [(4096, 6), (8192, 3), (2048, 8), (256, 4)])
 def test_bulk_copy_gather_is_bit_exact(fs, dim, dtype, tile, stages):
