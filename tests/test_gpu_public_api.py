@@ -316,12 +316,12 @@ def test_async_slice_tensors_against_compiled_reference(fs, data):
         assert torch.equal(g_[1].cpu(), w_[1]) and torch.equal(g_[2].cpu(), w_[2]), f"positions of request {i}"
 
 
-@pytest.mark.parametrize("dim,dtype", [(100, torch.float16), (50, torch.float32), (37, torch.float16)])
+@pytest.mark.parametrize("dim,dtype", [(100, torch.float16), (50, torch.float32), (62, torch.float16), (49, torch.float16)])
 @pytest.mark.parametrize("tile,stages", [(4096, 6), (1024, 4)])
 def test_bulk_copy_gather_of_pitched_rows(fs, dim, dtype, tile, stages):
     """Rows that are not multiples of 16 bytes in a 128-byte-multiple pitch (ogbn-products: 200 bytes
     in 256): the bulk flavour copies round_up(row, 16) bytes per row into shared memory and the warp
-    stores the dense rows (8- or 4-byte words; 74-byte rows are not eligible and take the LDG path)."""
+    stores the dense rows (8- or 4-byte words; 98-byte rows are not eligible and take the LDG path)."""
     from salient_plusplus_b200 import _lib
     from salient_plusplus_b200.fast_sampler import make_feature_map
     L = _lib.load()
