@@ -300,9 +300,10 @@ def distributed_binning(n_id, offsets, rank: int, world_size: int, x_gpu_rows: i
 #                stand-in with its published semantics) -> tests/golden/vip.npz, checked in
 #                tests/test_oracle_golden.py at the reference's fp32 precision.
 #   exact=False: driver/drivers/ddp.py:134-239 (get_frequency_tensors_fast, first-order form the
-#                driver actually uses).  PARITY UNPINNED: that function needs a CUDA device, an
-#                initialised process group and torch_scatter; it differs from the pinned form only
-#                in the per-neighbour term (:219-224 vs vip.py:166-172).
+#                driver actually uses).  PINNED: the function's own source text was executed here
+#                (tests/golden/make_golden_vip_driver.py: stand-ins for torch_scatter.segment_csr,
+#                dist.get_rank and the CUDA stream plumbing only, asserts stripped like the
+#                reference's PYTHONOPTIMIZE=1 launch) -> tests/golden/vip_driver.npz (fp64).
 # ---------------------------------------------------------------------------------------------
 def vip_probabilities(rowptr, col, train_idx, batch_size: int, fanouts, exact: bool = False) -> np.ndarray:
     rowptr, col = _i64(rowptr), _i64(col)

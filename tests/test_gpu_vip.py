@@ -27,6 +27,20 @@ def test_vip_exact_form_against_reference_golden(fi):
         assert np.max(np.abs(got - O.vip_probabilities(g["rowptr"], g["col"], g[f"train{p}"], 32, fanouts, exact=True))) < 1e-12
 
 
+@pytest.mark.parametrize("fi", [0, 1])
+def test_vip_first_order_form_against_reference_driver_golden(fi):
+    """The kernel's first-order form (what `bench.py` / create_vip_cache use) against the output of
+    the reference driver's own get_frequency_tensors_fast (tests/golden/vip_driver.npz, fp64)."""
+    import os
+    from salient_plusplus_b200 import vip
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vip_driver.npz"))
+    fanouts = g[f"fanouts{fi}"].tolist()
+    rowptr, col = torch.from_numpy(g["rowptr"]), torch.from_numpy(g["col"])
+    for p in range(4):
+        got = vip.vip_probabilities(rowptr, col, torch.from_numpy(g[f"train{p}"]), 32, fanouts).cpu().numpy()
+        assert np.max(np.abs(got - g[f"vip{fi}_{p}"])) < 1e-12
+
+
 @pytest.mark.parametrize("fanouts", [[15, 10, 5], [25, 15], [5]])
 def test_vip_probabilities(fanouts):
     from salient_plusplus_b200 import vip

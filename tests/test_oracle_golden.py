@@ -118,6 +118,17 @@ def test_mt19937_known_answer():
 
 
 @pytest.mark.parametrize("fi", [0, 1])
+def test_vip_first_order_form_against_the_reference_driver(fi):
+    """Golden vectors produced by executing the reference driver's own get_frequency_tensors_fast
+    (driver/drivers/ddp.py:134-239, fp64; tests/golden/make_golden_vip_driver.py)."""
+    g = np.load(os.path.join(G, "vip_driver.npz"))
+    fanouts = g[f"fanouts{fi}"].tolist()
+    for p in range(4):
+        got = O.vip_probabilities(g["rowptr"], g["col"], g[f"train{p}"], 32, fanouts, exact=False)
+        assert np.max(np.abs(got - g[f"vip{fi}_{p}"])) < 1e-14
+
+
+@pytest.mark.parametrize("fi", [0, 1])
 def test_vip_analytical_against_reference_module(fi):
     """Golden vectors produced by the reference's own caching/vip.py:vip_analytical (fp32)."""
     g = np.load(os.path.join(G, "vip.npz"))
