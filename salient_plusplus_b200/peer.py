@@ -33,7 +33,6 @@ from ._lib import SPP_MAX_PARTS, check
 _PINNED: Dict[int, torch.Tensor] = {}
 # (group id, peer rank) -> (descriptor, mapped pointer, offset)
 _IMPORTED: Dict[Tuple[int, int], Tuple[tuple, int, int]] = {}
-_GENERATION = [0]
 
 
 def export_handle(t: torch.Tensor) -> Tuple[bytes, int]:
@@ -76,7 +75,6 @@ def exchange_device_tables(local: torch.Tensor, group=None) -> Optional[List[int
     torch.cuda.synchronize()
     _PINNED[local.data_ptr()] = local
     handle, offset = export_handle(local)
-    _GENERATION[0] += 1
     mine = (socket.gethostname(), torch.cuda.current_device(), handle, offset, local.data_ptr())
     gathered: List[Optional[tuple]] = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
