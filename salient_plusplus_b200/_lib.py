@@ -14,6 +14,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_int, c_int32, c_int64, c_uin
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsalient_b200.so")
+HOST_EXT_PATH = os.path.join(_PKG, "_spp_host.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 ABI_VERSION = 2
@@ -108,6 +109,58 @@ def build_library(force: bool = False, quiet: bool = True) -> str:
     out = subprocess.DEVNULL if quiet else None
     subprocess.check_call(["make", "-C", CSRC, "-j", "4"], stdout=out)
     return LIB_PATH
+
+
+def build_host_extension(force: bool = False, quiet: bool = True) -> str:
+    """Compile ``csrc/host_session.cpp`` (the per-batch host path of a Session: pybind11 + libtorch,
+    no device code) into ``_spp_host.so`` next to the package with plain g++ -- in-tree, so the built
+    file travels with the source snapshot instead of living in a JIT cache."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    src = os.path.join(CSRC, "host_session.cpp")
+    hdr = os.path.join(os.path.dirname(_PKG), "include", "salient_b200.h")
+    if not force and os.path.exists(HOST_EXT_PATH) and \
+            os.path.getmtime(HOST_EXT_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return HOST_EXT_PATH
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+           "-DTORCH_EXTENSION_NAME=_spp_host", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           "-I" + os.path.dirname(hdr), "-I" + sysconfig.get_paths()["include"], "-I" + os.path.join(cuda_home, "include")]
+    cmd += ["-I" + p for p in ce.include_paths()]
+    cmd += [src, "-o", HOST_EXT_PATH + ".tmp"]
+    cmd += ["-L" + p for p in ce.library_paths()] + ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch", "-ltorch_python"]
+    if not quiet:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    os.replace(HOST_EXT_PATH + ".tmp", HOST_EXT_PATH)
+    return HOST_EXT_PATH
+
+
+_host = None
+
+
+def load_host():
+    """The ``_spp_host`` module (native per-batch host path).  Missing or stale builds raise: the
+    Session does not silently fall back to the interpreter path (``SPP_NATIVE_HOST=0`` selects it)."""
+    global _host
+    if _host is not None:
+        return _host
+    if not os.path.exists(HOST_EXT_PATH):
+        raise SalientB200Error(
+            f"{HOST_EXT_PATH} is missing: the host-path extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`); SPP_NATIVE_HOST=0 selects the "
+            "interpreter implementation of the same bookkeeping")
+    import importlib.util
+    import torch  # noqa: F401  (libtorch must be loaded before the extension resolves its symbols)
+    spec = importlib.util.spec_from_file_location("salient_plusplus_b200._spp_host", HOST_EXT_PATH)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if mod.ABI_VERSION != ABI_VERSION or mod.BATCH_JOB_BYTES != ctypes.sizeof(BatchJob):
+        raise SalientB200Error("_spp_host.so was built against a different salient_b200.h: rebuild it")
+    _host = mod
+    return mod
 
 
 def load() -> ctypes.CDLL:

@@ -715,6 +715,34 @@ def clear_slot_pool() -> None:
     _SLOT_POOL.clear()
 
 
+def host_session_spec(*, device, n_hops: int, num_parts: int, layout, has_x: bool, feat_dim: int, feat_dtype,
+                      y: Optional[torch.Tensor], y_in_arena: bool, ranges, batch_edges, idx_host_ptr: int,
+                      idx_dev_ptr: int, executor, entry_points, slots, e_id: torch.Tensor) -> dict:
+    """The construction record of ``_spp_host.HostSession`` (csrc/host_session.cpp).  ``layout`` =
+    ``Session._layout(None)``; ``num_parts`` < 0: not distributed; ``entry_points`` = the ctypes
+    functions (submit, poll, wait, last_error) -- of libsalient_b200.so in a Session, of a
+    recording stand-in in the CPU tests; ``slots``: objects with ``cjob`` / ``meta_host`` /
+    ``seeds`` / ``stream_raw`` (a ``_Slot``)."""
+    a_off, a_nid, a_y, a_words, node_bound = layout
+    fn_addr = [ctypes.cast(f, ctypes.c_void_p).value for f in entry_points]
+    return {
+        "device": device, "n_hops": int(n_hops), "num_parts": int(num_parts),
+        "hop_offsets": [(int(r), int(c)) for r, c in a_off], "nid_offset": int(a_nid), "y_offset": int(a_y),
+        "arena_words": int(a_words), "node_bound": int(node_bound),
+        "has_x": bool(has_x), "feat_dim": int(feat_dim), "feat_dtype": feat_dtype,
+        "has_y": y is not None, "y_in_arena": bool(y_in_arena),
+        "y_cols": int(y.size(-1)) if y is not None else 0, "y_dtype": y.dtype if y is not None else torch.int64,
+        "ranges": [(int(a), int(b)) for a, b in ranges],
+        "batch_edges": [int(v) for v in batch_edges] if batch_edges is not None else [],
+        "idx_host_ptr": int(idx_host_ptr or 0), "idx_dev_ptr": int(idx_dev_ptr or 0),
+        "executor": int(executor), "submit_fn": fn_addr[0], "poll_fn": fn_addr[1], "wait_fn": fn_addr[2],
+        "last_error_fn": fn_addr[3],
+        "slots": [(ctypes.addressof(s.cjob), s.meta_host.data_ptr(), s.seeds.data_ptr(), int(s.stream_raw[0]),
+                   int(s.stream_raw[1]), int(s.stream_raw[2])) for s in slots],
+        "e_id": e_id, "error_cls": SalientB200Error,
+    }
+
+
 class Session:
     """``fast_sampler.Session`` (fast_sampler/fast_sampler.cpp:533-936, bound at :1310-1338)."""
 
@@ -744,8 +772,9 @@ class Session:
         self._num_total = len(self._ranges)
         self._num_consumed = 0
         self._next = 0
-        self.total_blocked_dur = datetime.timedelta(0)
-        self.total_blocked_occasions = 0
+        self._blocked_dur = datetime.timedelta(0)
+        self._blocked_occasions = 0
+        self._native = None
         self._full = any(s < 0 for s in self._sizes)
         # Layer-wise inference (driver/models.py:455-480) samples ONE full-neighbourhood hop per
         # batch: its edge count is the degree sum of the seeds, known before anything is launched,
@@ -812,8 +841,15 @@ class Session:
         for s in self._slots:
             s.stream.wait_stream(cur)
         if _t: _t.append(time.perf_counter())
-        while self._free and self._next < self._num_total:
-            self._enqueue()
+        # The per-batch bookkeeping (output allocation, job fill, submit, view cutting) runs in the
+        # native host path (csrc/host_session.cpp) whenever batches go through the executor;
+        # SPP_NATIVE_HOST=0 keeps the interpreter implementation below (_enqueue / _finalize).
+        if self._executor is not None and os.environ.get("SPP_NATIVE_HOST", "1") != "0":
+            self._native = _lib.load_host().HostSession(self._native_spec())
+            self._native.fill()
+        else:
+            while self._free and self._next < self._num_total:
+                self._enqueue()
         if _t:
             _t.append(time.perf_counter())
             print("[spp] Session init us: graph/idx %.0f features %.0f slots/jobs %.0f first enqueues %.0f" % tuple(
@@ -995,6 +1031,19 @@ class Session:
         j.n_id_out = slot.job_dev.data_ptr() if cfg.distributed else None   # placeholder, non-NULL
         j.batch_size = j.batch_size_cap
         check(self._lib.spp_batch_prepare(ctypes.byref(j)), "spp_batch_prepare")
+
+    def _native_spec(self) -> dict:
+        """Everything csrc/host_session.cpp needs to run this Session's batches (see host_session_spec)."""
+        lib, cfg = self._lib, self._config
+        fdim, fdtype = self._feat_shape
+        return host_session_spec(
+            device=self._device, n_hops=len(self._sizes), num_parts=self._P if cfg.distributed else -1, layout=self._lay,
+            has_x=bool(self._slots[0].cjob.feature_mode), feat_dim=fdim, feat_dtype=fdtype, y=self._y,
+            y_in_arena=self._y_in_arena, ranges=self._ranges, batch_edges=self._batch_edges,
+            idx_host_ptr=self._idx_host_ptr if self._idx_host is not None else 0,
+            idx_dev_ptr=self._idx.data_ptr() if self._idx is not None else 0, executor=self._executor,
+            entry_points=(lib.spp_executor_submit, lib.spp_executor_poll, lib.spp_executor_wait, lib.spp_last_error),
+            slots=self._slots, e_id=_empty_eid(self._device))
 
     def _prime_allocator(self, slot: "_Slot", blocks: int = 3):
         """Per-batch outputs are allocated at their upper bounds from PyTorch's caching allocator
@@ -1209,17 +1258,7 @@ class Session:
             b.idx_range = (start, stop)
             b.sliced_cpu_labels = job["y"]
             b.x = (job["x"][:nb] if job["x"].size(0) > nb else job["x"]) if "x" in job else None
-            fdim, fdtype = self._feat_shape
-            if self._x_cpu_dev is not None:
-                # compatibility with gpu_percent < 1 (fast_sampler.cpp:1041-1052,1142-1155): rows of
-                # local nodes whose local id lies in the x_cpu tail, in partition_nids[rank] order
-                loc = b.partition_nids[self._rank] - self._off[self._rank]
-                sel = loc[loc >= self._x_gpu_rows] - self._x_gpu_rows
-                b.sliced_cpu_features = serial_index(self._x_cpu_dev, sel)
-            else:
-                b.sliced_cpu_features = torch.empty((0, fdim), dtype=fdtype, device=self._device)
-            if cfg.count_remote_frequency and not cfg.use_cache:
-                self._count_remote(b)
+            self._attach_host_rows(b)
             out = b
         self._num_consumed += 1
         self._free.append(slot)
@@ -1233,6 +1272,12 @@ class Session:
         if self._released:
             return
         self._released = True
+        if self._native is not None:
+            abandoned = self._native.in_flight > 0  # Session dropped before its last batch
+            self._native.release()                  # waits for that work and drops its outputs
+            if abandoned:
+                for s in self._slots:
+                    s.stream.synchronize()
         for s in self._pending:  # abandoned in-flight work (Session dropped early)
             if s.ticket is not None:
                 self._lib.spp_executor_wait(self._executor, s.ticket)
@@ -1278,6 +1323,8 @@ class Session:
             check(self._lib.spp_executor_wait(self._executor, slot.ticket), "spp_executor_wait")
 
     def _get(self, blocking: bool):
+        if self._native is not None:
+            return self._get_native(blocking)
         if self._num_consumed == self._num_total:
             return None
         slot = self._pending[0]
@@ -1293,8 +1340,8 @@ class Session:
                 print("[spp] batch %d: queued %.0f us, issuing %.0f us, issue->complete %.0f us (waited %.0f us)" % (
                     self._num_consumed, (tt[1] - tt[0]) * 1e6, (tt[2] - tt[1]) * 1e6, (now - tt[2]) * 1e6,
                     (time.perf_counter() - t0) * 1e6), flush=True)
-            self.total_blocked_dur += datetime.timedelta(microseconds=int((time.perf_counter() - t0) * 1e6))
-            self.total_blocked_occasions += 1
+            self._blocked_dur += datetime.timedelta(microseconds=int((time.perf_counter() - t0) * 1e6))
+            self._blocked_occasions += 1
         self._pending.popleft()
         return self._finalize(slot)
 
@@ -1318,10 +1365,59 @@ class Session:
             raise RuntimeError("blocking_get_batch_distributed called on a non-distributed Session")
         return self._get(True)
 
+    def _get_native(self, blocking: bool):
+        """One batch from the native host path, wrapped in the containers the Python API returns."""
+        nat = self._native
+        r = nat.get(blocking)
+        if r is None:
+            return None
+        cfg = self._config
+        if not cfg.distributed:
+            out = OwnedSample(r[:4])
+            out.owners = r[4]
+        else:
+            b = ProtoDistributedBatch()
+            (b.n_id, b.partition_nids, b.cached_nids, b.perm_partition_to_mfg, b.adjs, b.idx_range,
+             b.sliced_cpu_labels, b.x, b.owners) = r
+            self._attach_host_rows(b)
+            out = b
+        self._num_consumed = nat.consumed
+        if self._num_consumed == self._num_total:
+            self._release_slots()
+        return out
+
+    def _attach_host_rows(self, b: "ProtoDistributedBatch") -> None:
+        """``sliced_cpu_features`` (+ the remote-frequency statistics) of a distributed batch."""
+        fdim, fdtype = self._feat_shape
+        if self._x_cpu_dev is not None:
+            # compatibility with gpu_percent < 1 (fast_sampler.cpp:1041-1052,1142-1155): rows of
+            # local nodes whose local id lies in the x_cpu tail, in partition_nids[rank] order
+            loc = b.partition_nids[self._rank] - self._off[self._rank]
+            sel = loc[loc >= self._x_gpu_rows] - self._x_gpu_rows
+            b.sliced_cpu_features = serial_index(self._x_cpu_dev, sel)
+        else:
+            b.sliced_cpu_features = torch.empty((0, fdim), dtype=fdtype, device=self._device)
+        if self._config.count_remote_frequency and not self._config.use_cache:
+            self._count_remote(b)
+
+    @property
+    def total_blocked_dur(self) -> datetime.timedelta:
+        if self._native is not None:
+            return datetime.timedelta(microseconds=self._native.blocked_us)
+        return self._blocked_dur
+
+    @property
+    def total_blocked_occasions(self) -> int:
+        return self._native.blocked_occasions if self._native is not None else self._blocked_occasions
+
     num_consumed_batches = property(lambda self: self._num_consumed)
     num_total_batches = property(lambda self: self._num_total)
-    approx_num_complete_batches = property(lambda self: self._num_consumed + sum(
-        1 for s in self._pending if self._slot_done(s)))
+
+    @property
+    def approx_num_complete_batches(self) -> int:
+        if self._native is not None:
+            return self._native.complete_count()
+        return self._num_consumed + sum(1 for s in self._pending if self._slot_done(s))
 
     # -- async_slice_tensors (fast_sampler.cpp:720-775): serve other ranks' requests for rows that
     #    the reference keeps on the host; here those rows are in HBM too -----------------------
