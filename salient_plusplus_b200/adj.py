@@ -18,10 +18,20 @@ except Exception:  # noqa: BLE001
     class SparseTensor:  # type: ignore
         """CSR holder with the constructor signature fast_trainer/samplers.py:25-27 uses."""
 
+        __slots__ = ("_rowptr", "_row", "_col", "_value", "_sparse_sizes")
+
         def __init__(self, rowptr=None, row=None, col=None, value=None, sparse_sizes=None, is_sorted=False,
                      trust_data=False):
             self._rowptr, self._row, self._col, self._value = rowptr, row, col, value
             self._sparse_sizes = (int(sparse_sizes[0]), int(sparse_sizes[1]))
+
+        @classmethod
+        def from_csr(cls, rowptr, col, sparse_sizes):
+            """Same object as ``SparseTensor(rowptr=..., col=..., sparse_sizes=..., is_sorted=True,
+            trust_data=True)`` without the keyword parsing (one per hop and mini-batch)."""
+            st = cls.__new__(cls)
+            st._rowptr, st._row, st._col, st._value, st._sparse_sizes = rowptr, None, col, None, sparse_sizes
+            return st
 
         def csr(self):
             return self._rowptr, self._col, self._value
@@ -81,8 +91,15 @@ class Adj(NamedTuple):
             self.e_id.record_stream(stream)
 
 
+_new_adj = tuple.__new__
+
+
 def Adj__from_fast_sampler(adj) -> Adj:
     """fast_trainer/samplers.py:22-30"""
     rowptr, col, e_id, sparse_sizes = adj
-    return Adj(SparseTensor(rowptr=rowptr, row=None, col=col, value=None, sparse_sizes=tuple(sparse_sizes),
-                            is_sorted=True, trust_data=True), e_id, (sparse_sizes[1], sparse_sizes[0]))
+    if HAVE_TORCH_SPARSE:
+        adj_t = SparseTensor(rowptr=rowptr, row=None, col=col, value=None, sparse_sizes=tuple(sparse_sizes),
+                             is_sorted=True, trust_data=True)
+    else:
+        adj_t = SparseTensor.from_csr(rowptr, col, (int(sparse_sizes[0]), int(sparse_sizes[1])))
+    return _new_adj(Adj, (adj_t, e_id, (sparse_sizes[1], sparse_sizes[0])))

@@ -53,6 +53,29 @@ struct Slot {
   int64_t start = 0, stop = 0;
 };
 
+// A contiguous window of `base`'s storage as a tensor of its own: `sizes` elements (row-major, at most
+// four dimensions) starting `offset` elements into the view `base`.  Built the way ATen's own
+// alias_with_sizes_and_strides builds a view -- a TensorImpl on the shared Storage -- instead of
+// through narrow()/view() and the dispatcher: a batch is cut into 8-20 such windows and each dispatched
+// view op costs microseconds of host time, which is the whole budget on the small graph shapes.
+at::Tensor window(const at::Tensor& base, int64_t offset, c10::IntArrayRef sizes) {
+  auto t = at::detail::make_tensor<c10::TensorImpl>(c10::TensorImpl::VIEW, c10::Storage(base.storage()), base.key_set(),
+                                                    base.dtype());
+  auto* impl = t.unsafeGetTensorImpl();
+  impl->set_storage_offset(base.storage_offset() + offset);
+  int64_t strides[4] = {1, 1, 1, 1};
+  for (int d = (int)sizes.size() - 2; d >= 0; --d) strides[d] = strides[d + 1] * std::max<int64_t>(sizes[d + 1], 1);
+  impl->set_sizes_and_strides(sizes, c10::IntArrayRef(strides, sizes.size()));
+  return t;
+}
+at::Tensor window(const at::Tensor& base, int64_t offset, int64_t rows) {
+  return window(base, offset, c10::IntArrayRef(&rows, 1));
+}
+at::Tensor window(const at::Tensor& base, int64_t offset, int64_t rows, int64_t cols) {
+  const int64_t sizes[2] = {rows, cols};
+  return window(base, offset, c10::IntArrayRef(sizes, 2));
+}
+
 template <typename T>
 T item(const py::dict& d, const char* key) {
   if (!d.contains(key)) throw std::invalid_argument(std::string("HostSession: missing field '") + key + "'");
@@ -213,7 +236,7 @@ class HostSession {
       s.y = s.y_separate ? at::empty({bs, y_cols_}, dev_opts.dtype(y_dtype_)) : at::Tensor();
     }
     if (has_y_ && y_in_arena_)  // int64 labels live at the tail of the arena
-      s.y = s.arena.narrow(0, y_off_, bs * y_cols_).view({bs, y_cols_});
+      s.y = window(s.arena, y_off_, bs, y_cols_);
     int64_t* base = s.arena.data_ptr<int64_t>();
     for (int h = 0; h < n_hops_; ++h) {
       j.out_rowptr[h] = base + hop_off_[h].first;
@@ -263,35 +286,44 @@ class HostSession {
     py::list adjs(L);
     for (int h = 0; h < L; ++h) {
       const int64_t T = m[SPP_META_NODES(h)], E = m[SPP_META_EDGES(h)];
-      adjs[L - 1 - h] = py::make_tuple(s.arena.narrow(0, hop_off_[h].first, T + 1), s.arena.narrow(0, hop_off_[h].second, E),
+      adjs[L - 1 - h] = py::make_tuple(window(s.arena, hop_off_[h].first, T + 1), window(s.arena, hop_off_[h].second, E),
                                        e_id_, py::make_tuple(T, m[SPP_META_NODES(h + 1)]));
     }
     py::tuple range = py::make_tuple(s.start, s.stop);
-    py::object y = s.y.defined() ? py::cast(s.y) : py::none();
+    py::object y = py::none(), y_flat = py::none();
+    if (s.y.defined()) {
+      y = py::cast(s.y);
+      // the labels as the training loop takes them: y.squeeze() (fast_trainer/samplers.py:233,254)
+      int64_t dims[2];
+      int nd = 0;
+      for (int64_t d : s.y.sizes())
+        if (d != 1) dims[nd++] = d;
+      y_flat = py::cast(nd == 2 ? s.y : window(s.y, 0, c10::IntArrayRef(dims, nd)));
+    }
     py::object out;
     if (parts_ < 0) {
       at::Tensor x = s.x.defined() ? s.x : at::empty({0, feat_dim_}, at::TensorOptions().device(device_).dtype(feat_dtype_));
       py::tuple owners = s.y_separate ? py::make_tuple(x, s.arena, s.y) : py::make_tuple(x, s.arena);
-      out = py::make_tuple(x.size(0) > nb ? x.narrow(0, 0, nb) : x, y, adjs, range, owners);
+      out = py::make_tuple(x.size(0) > nb ? window(x, 0, nb, feat_dim_) : x, y, adjs, range, owners, y_flat);
     } else {
       const int64_t* counts = m + SPP_META_WORDS;
       py::list buckets(parts_);
       int64_t pos = nid_off_ + node_bound_;
       for (int p = 0; p < parts_; ++p) {
-        buckets[p] = s.arena.narrow(0, pos, counts[p]);
+        buckets[p] = window(s.arena, pos, counts[p]);
         pos += counts[p];
       }
-      at::Tensor cached = s.arena.narrow(0, pos, counts[parts_]);
+      at::Tensor cached = window(s.arena, pos, counts[parts_]);
       py::object x = py::none();
       py::tuple owners;
       if (s.x.defined()) {
-        x = py::cast(s.x.size(0) > nb ? s.x.narrow(0, 0, nb) : s.x);
+        x = py::cast(s.x.size(0) > nb ? window(s.x, 0, nb, feat_dim_) : s.x);
         owners = s.y_separate ? py::make_tuple(s.arena, s.x, s.y) : py::make_tuple(s.arena, s.x);
       } else {
         owners = s.y_separate ? py::make_tuple(s.arena, s.y) : py::make_tuple(s.arena);
       }
-      out = py::make_tuple(s.arena.narrow(0, nid_off_, nb), buckets, cached,
-                           s.arena.narrow(0, nid_off_ + 2 * node_bound_, nb), adjs, range, y, x, owners);
+      out = py::make_tuple(window(s.arena, nid_off_, nb), buckets, cached, window(s.arena, nid_off_ + 2 * node_bound_, nb),
+                           adjs, range, y, x, owners, y_flat);
     }
     drop(s);
     return out;

@@ -74,8 +74,10 @@ def current_stream_cached(device_index: int) -> torch.cuda.Stream:
 
 class OwnedSample(tuple):
     """The tuple a non-distributed Session returns, plus ``owners``: the distinct allocations its
-    tensors are views of (``record_stream`` on those covers every view)."""
+    tensors are views of (``record_stream`` on those covers every view), and ``y_flat``: the labels
+    already squeezed the way the training loop takes them (None: squeeze ``[1]`` yourself)."""
     owners: tuple = ()
+    y_flat = None
 
 
 _RESIDENT: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -602,6 +604,7 @@ class ProtoDistributedBatch:
         self.n_id = None
         self.x = None
         self.owners: tuple = ()  # distinct allocations the tensors above are views of
+        self.y_flat = None       # sliced_cpu_labels.squeeze(), when the native host path made it
 
 
 def _batch_ranges(n: int, cfg: Config) -> List[Tuple[int, int]]:
@@ -1374,11 +1377,11 @@ class Session:
         cfg = self._config
         if not cfg.distributed:
             out = OwnedSample(r[:4])
-            out.owners = r[4]
+            out.owners, out.y_flat = r[4], r[5]
         else:
             b = ProtoDistributedBatch()
             (b.n_id, b.partition_nids, b.cached_nids, b.perm_partition_to_mfg, b.adjs, b.idx_range,
-             b.sliced_cpu_labels, b.x, b.owners) = r
+             b.sliced_cpu_labels, b.x, b.owners, b.y_flat) = r
             self._attach_host_rows(b)
             out = b
         self._num_consumed = nat.consumed

@@ -59,6 +59,8 @@ class ProtoDistributedBatch(NamedTuple):
     x: Optional[torch.Tensor] = None
     # the distinct allocations every tensor above is a view of (record_stream on those is enough)
     owners: tuple = ()
+    # sliced_cpu_labels already squeezed (None: not precomputed)
+    y_flat: Optional[torch.Tensor] = None
 
     @classmethod
     def from_fast_sampler(cls, batch):
@@ -66,7 +68,8 @@ class ProtoDistributedBatch(NamedTuple):
             raise AssertionError("distributed batch without sliced_cpu_features")
         return cls(batch.partition_nids, batch.sliced_cpu_features, batch.sliced_cpu_labels, batch.cached_nids,
                    batch.perm_partition_to_mfg, _wrap(batch.adjs), _as_slice(batch.idx_range),
-                   getattr(batch, "n_id", None), getattr(batch, "x", None), getattr(batch, "owners", ()))
+                   getattr(batch, "n_id", None), getattr(batch, "x", None), getattr(batch, "owners", ()),
+                   getattr(batch, "y_flat", None))
 
     def record_stream(self, stream):
         _mark(stream, self.owners, (*self.partition_nids, self.perm_partition_to_mfg, self.n_id, self.x), self.adjs)
@@ -124,7 +127,8 @@ class PreparedBatch(NamedTuple):
         feats, labels, raw, rng = prepared_sample
         owners = getattr(prepared_sample, "owners", None)
         kind = OwnedPreparedBatch if (owners and cls is PreparedBatch) else cls
-        made = kind(feats, _flat_labels(labels), _wrap(raw), _as_slice(rng))
+        flat = getattr(prepared_sample, "y_flat", None)
+        made = kind(feats, flat if flat is not None else _flat_labels(labels), _wrap(raw), _as_slice(rng))
         if kind is OwnedPreparedBatch:
             made.owners = owners
         return made

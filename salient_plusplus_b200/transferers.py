@@ -124,12 +124,14 @@ class DeviceDistributedPrefetcher(DeviceIterator):
                 "partition count and no Config.partition_tables); use NcclAllToAllPrefetcher for the "
                 "all_to_all comparison path")
         self.NUMBER_OF_SENT_BYTES += _feature_bytes(batch, self.rank, batch.x.size(1) * batch.x.element_size())
-        y = batch.sliced_cpu_labels
+        y = batch.y_flat
+        if y is None and batch.sliced_cpu_labels is not None:
+            y = batch.sliced_cpu_labels.squeeze()
         if batch.owners:
-            b = OwnedPreparedBatch(batch.x, y.squeeze() if y is not None else None, batch.adjs, batch.idx_range)
+            b = OwnedPreparedBatch(batch.x, y, batch.adjs, batch.idx_range)
             b.owners = batch.owners
             return b
-        return PreparedBatch(batch.x, y.squeeze() if y is not None else None, batch.adjs, batch.idx_range)
+        return PreparedBatch(batch.x, y, batch.adjs, batch.idx_range)
 
     def preload(self, timing=True):
         batch = next(self.it, None)

@@ -141,7 +141,7 @@ def test_nondistributed_batches_in_order(fx, host, polls):
         r = hs.get(True)
         if r is None:
             break
-        x, y, adjs, rng, owners = r
+        x, y, adjs, rng, owners, y_flat = r
         st, en = ranges[got]
         assert rng == (st, en)
         seed0 = int(idx[st])
@@ -149,6 +149,7 @@ def test_nondistributed_batches_in_order(fx, host, polls):
         assert x.shape == (nb, 8) and x.dtype == torch.float16
         assert x.view(torch.uint8)[:, 0].tolist() == [(seed0 + i) & 0xff for i in range(nb)]
         assert y.shape == (en - st, 1) and y.view(-1).tolist() == (3 * idx[st:en]).tolist()
+        assert y_flat.shape == y.squeeze().shape and torch.equal(y_flat, y.squeeze()) and y_flat.data_ptr() == y.data_ptr()
         assert len(owners) == 2 and owners[0].size(0) >= nb                   # x block + arena (int64 labels live in the arena)
         assert owners[1].data_ptr() <= adjs[0][0].data_ptr() < owners[1].data_ptr() + owners[1].numel() * 8
         assert owners[1].data_ptr() <= y.data_ptr() < owners[1].data_ptr() + owners[1].numel() * 8
@@ -192,7 +193,7 @@ def test_job_fields_per_batch(fx, host):
     hs.get(True)
     j = fx.fx_last_job(ex).contents
     assert j.batch_size == 8 and j.rng_seed == 40 * 17 + 5                     # ragged last batch
-    x, y, adjs, rng, _owners = hs.get(True)
+    x, y, adjs, rng, _owners, _yf = hs.get(True)
     assert rng == (32, 40) and y.shape == (8, 1) and adjs[-1][3][0] == 8
     fx.fx_destroy(ex)
 
@@ -202,8 +203,8 @@ def test_device_resident_seeds_and_separate_labels(fx, host):
     hs.fill()
     j = fx.fx_last_job(ex).contents
     assert j.seeds_host is None and j.seeds_dev == idx.data_ptr() + 8 * 16     # used in place
-    x, y, adjs, rng, owners = hs.get(True)
-    assert y.dtype == torch.int32 and y.shape == (16, 1)
+    x, y, adjs, rng, owners, y_flat = hs.get(True)
+    assert y.dtype == torch.int32 and y.shape == (16, 1) and y_flat.shape == (16,) and y_flat.data_ptr() == y.data_ptr()
     assert len(owners) == 3 and owners[2].data_ptr() == y.data_ptr()           # labels are their own allocation
     fx.fx_destroy(ex)
 
@@ -211,7 +212,7 @@ def test_device_resident_seeds_and_separate_labels(fx, host):
 def test_no_feature_table(fx, host):
     hs, ex, ranges, idx, keep = make(fx, host, feat=False, n_seeds=16)
     hs.fill()
-    x, y, adjs, rng, owners = hs.get(True)
+    x, y, adjs, rng, owners, y_flat = hs.get(True)
     assert x.shape == (0, 8) and x.dtype == torch.float16
     assert fx.fx_last_job(ex).contents.x_out is None
     fx.fx_destroy(ex)
@@ -222,7 +223,7 @@ def test_distributed_pieces(fx, host, P):
     hs, ex, ranges, idx, (caps, _keep) = make(fx, host, P=P, n_seeds=48, L=3)
     hs.fill()
     for k in range(3):
-        n_id, parts, cached, perm, adjs, rng, y, x, owners = hs.get(True)
+        n_id, parts, cached, perm, adjs, rng, y, x, owners, y_flat = hs.get(True)
         st, en = ranges[k]
         seed0 = int(idx[st])
         nb = check_structure(adjs, seed0, en - st, caps)
@@ -247,7 +248,7 @@ def test_layerwise_capacity_per_batch(fx, host):
     hs.fill()
     for cap in (5, 0, 31):
         assert fx.fx_last_job(ex).contents.out_col_cap[0] == cap
-        x, y, adjs, rng, _owners = hs.get(True)
+        x, y, adjs, rng, _owners, _yf = hs.get(True)
         assert adjs[0][1].numel() == cap and adjs[0][3] == (16, 16 + cap // 2)
     fx.fx_destroy(ex)
 
