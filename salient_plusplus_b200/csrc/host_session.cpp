@@ -9,9 +9,11 @@
 // interpreter, not by the GPU.  This file is that bookkeeping as one native call per batch:
 //
 //   fill()          for every free slot: allocate the batch's outputs from PyTorch's caching allocator
-//                   on the slot's stream (one int64 arena + x + y, at their upper bounds), write the
-//                   per-batch fields of the slot's spp_batch_job and hand it to the executor thread
-//                   of libsalient_b200.so (spp_executor_submit);
+//                   on the slot's stream -- ONE block per batch holding the int64 arena, x and y at
+//                   their upper bounds (a block handed to the consumer costs a record_stream, and when
+//                   it is freed an event record + queries inside the allocator: per block, not per
+//                   byte) -- write the per-batch fields of the slot's spp_batch_job and hand it to the
+//                   executor thread of libsalient_b200.so (spp_executor_submit);
 //   get(blocking)   poll / wait for the oldest in-flight batch (in idx_range order, like
 //                   fast_sampler.cpp:672-712), read its pinned size block, cut the exact-size views
 //                   (rowptr / col per hop, n_id, partition buckets, cached ids, perm), re-arm the
@@ -48,8 +50,8 @@ struct Slot {
   int64_t* seeds_dev = nullptr;   // device staging buffer of host seeds
   std::optional<c10::Stream> stream;
   uint64_t ticket = 0;
-  at::Tensor arena, x, y;
-  bool y_separate = false;        // y is its own allocation (not a view of the arena)
+  at::Tensor block;               // the batch's single allocation (bytes)
+  at::Tensor arena, x, y;         // typed windows of it: int64 structure arena, features, labels
   int64_t start = 0, stop = 0;
 };
 
@@ -75,6 +77,20 @@ at::Tensor window(const at::Tensor& base, int64_t offset, int64_t rows, int64_t 
   const int64_t sizes[2] = {rows, cols};
   return window(base, offset, c10::IntArrayRef(sizes, 2));
 }
+
+// Same, for a window of another element type: `byte_offset` bytes into the byte block `block`.
+at::Tensor typed_window(const at::Tensor& block, int64_t byte_offset, at::ScalarType dtype, c10::IntArrayRef sizes) {
+  auto t = at::detail::make_tensor<c10::TensorImpl>(c10::TensorImpl::VIEW, c10::Storage(block.storage()), block.key_set(),
+                                                    c10::scalarTypeToTypeMeta(dtype));
+  auto* impl = t.unsafeGetTensorImpl();
+  impl->set_storage_offset((block.storage_offset() + byte_offset) / (int64_t)c10::elementSize(dtype));
+  int64_t strides[4] = {1, 1, 1, 1};
+  for (int d = (int)sizes.size() - 2; d >= 0; --d) strides[d] = strides[d + 1] * std::max<int64_t>(sizes[d + 1], 1);
+  impl->set_sizes_and_strides(sizes, c10::IntArrayRef(strides, sizes.size()));
+  return t;
+}
+
+inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 template <typename T>
 T item(const py::dict& d, const char* key) {
@@ -144,6 +160,15 @@ class HostSession {
     if (slots_.empty()) throw std::invalid_argument("HostSession: no slots");
     for (auto& s : slots_) free_.push_back(&s);
     total_ = (int64_t)ranges_.size();
+    // byte layout of a batch's block: [arena int64 | pad | x | pad | y (labels that are not int64)]
+    int64_t max_bs = 0;
+    for (const auto& r : ranges_) max_bs = std::max(max_bs, r.second - r.first);
+    y_separate_ = has_y_ && !y_in_arena_;
+    x_byte_off_ = round_up(arena_words_ * 8, 256);
+    const int64_t x_bytes = has_x_ ? node_bound_ * feat_dim_ * (int64_t)c10::elementSize(feat_dtype_) : 0;
+    y_byte_off_ = round_up(x_byte_off_ + x_bytes, 256);
+    block_bytes_ = y_byte_off_ + (y_separate_ ? max_bs * y_cols_ * (int64_t)c10::elementSize(y_dtype_) : 0);
+    if (block_bytes_ < 8) block_bytes_ = 8;
   }
 
   // enqueue batches while a slot is free (Session._enqueue)
@@ -203,6 +228,7 @@ class HostSession {
   int64_t blocked_us() const { return blocked_us_; }
   int64_t blocked_occasions() const { return blocked_occasions_; }
   int64_t in_flight() const { return (int64_t)pending_.size(); }
+  int64_t block_bytes() const { return block_bytes_; }
 
  private:
   [[noreturn]] void fail(const char* what, int rc) {
@@ -213,6 +239,7 @@ class HostSession {
   }
 
   static void drop(Slot& s) {
+    s.block = at::Tensor();
     s.arena = at::Tensor();
     s.x = at::Tensor();
     s.y = at::Tensor();
@@ -224,19 +251,21 @@ class HostSession {
     const int64_t b = next_;
     const int64_t start = ranges_[b].first, stop = ranges_[b].second, bs = stop - start;
     spp_batch_job& j = *s.job;
-    const auto dev_opts = at::TensorOptions().device(device_);
     {
-      // the outputs belong to the slot's stream (caching-allocator ownership)
+      // the block belongs to the slot's stream (caching-allocator ownership)
       c10::cuda::OptionalCUDAStreamGuard guard;
       if (s.stream) guard.reset_stream(c10::cuda::CUDAStream(*s.stream));
-      // one allocation for every structure output of the batch; exact-size views are cut in finalize()
-      s.arena = at::empty({arena_words_}, dev_opts.dtype(at::kLong));
-      s.x = has_x_ ? at::empty({node_bound_, feat_dim_}, dev_opts.dtype(feat_dtype_)) : at::Tensor();
-      s.y_separate = has_y_ && !y_in_arena_;
-      s.y = s.y_separate ? at::empty({bs, y_cols_}, dev_opts.dtype(y_dtype_)) : at::Tensor();
+      s.block = at::empty({block_bytes_}, at::TensorOptions().device(device_).dtype(at::kByte));
     }
-    if (has_y_ && y_in_arena_)  // int64 labels live at the tail of the arena
+    // exact-size views are cut in finalize(); these are the upper-bound windows the kernels write
+    s.arena = typed_window(s.block, 0, at::kLong, {arena_words_});
+    s.x = typed_window(s.block, x_byte_off_, feat_dtype_, {has_x_ ? node_bound_ : 0, feat_dim_});
+    if (y_separate_)
+      s.y = typed_window(s.block, y_byte_off_, y_dtype_, {bs, y_cols_});
+    else if (has_y_)  // int64 labels live at the tail of the arena
       s.y = window(s.arena, y_off_, bs, y_cols_);
+    else
+      s.y = at::Tensor();
     int64_t* base = s.arena.data_ptr<int64_t>();
     for (int h = 0; h < n_hops_; ++h) {
       j.out_rowptr[h] = base + hop_off_[h].first;
@@ -253,7 +282,7 @@ class HostSession {
     }
     j.batch_size = bs;
     j.rng_seed = (uint64_t)(stop * 17 + 5) & 0xFFFFFFFFull;  // fast_sampler.cpp:994
-    j.x_out = s.x.defined() ? s.x.data_ptr() : nullptr;
+    j.x_out = has_x_ ? s.x.data_ptr() : nullptr;
     j.y_out = (s.y.defined() && bs) ? s.y.data_ptr() : nullptr;
     if (parts_ >= 0) {
       j.n_id_out = base + nid_off_;
@@ -301,10 +330,10 @@ class HostSession {
       y_flat = py::cast(nd == 2 ? s.y : window(s.y, 0, c10::IntArrayRef(dims, nd)));
     }
     py::object out;
+    // every tensor of the batch is a view of the one block: record_stream on it covers them all
+    py::tuple owners = py::make_tuple(s.block);
     if (parts_ < 0) {
-      at::Tensor x = s.x.defined() ? s.x : at::empty({0, feat_dim_}, at::TensorOptions().device(device_).dtype(feat_dtype_));
-      py::tuple owners = s.y_separate ? py::make_tuple(x, s.arena, s.y) : py::make_tuple(x, s.arena);
-      out = py::make_tuple(x.size(0) > nb ? window(x, 0, nb, feat_dim_) : x, y, adjs, range, owners, y_flat);
+      out = py::make_tuple(s.x.size(0) > nb ? window(s.x, 0, nb, feat_dim_) : s.x, y, adjs, range, owners, y_flat);
     } else {
       const int64_t* counts = m + SPP_META_WORDS;
       py::list buckets(parts_);
@@ -314,14 +343,8 @@ class HostSession {
         pos += counts[p];
       }
       at::Tensor cached = window(s.arena, pos, counts[parts_]);
-      py::object x = py::none();
-      py::tuple owners;
-      if (s.x.defined()) {
-        x = py::cast(s.x.size(0) > nb ? window(s.x, 0, nb, feat_dim_) : s.x);
-        owners = s.y_separate ? py::make_tuple(s.arena, s.x, s.y) : py::make_tuple(s.arena, s.x);
-      } else {
-        owners = s.y_separate ? py::make_tuple(s.arena, s.y) : py::make_tuple(s.arena);
-      }
+      py::object x = py::none();  // no reachable feature tables: the all_to_all prefetcher gathers x
+      if (has_x_) x = py::cast(s.x.size(0) > nb ? window(s.x, 0, nb, feat_dim_) : s.x);
       out = py::make_tuple(window(s.arena, nid_off_, nb), buckets, cached, window(s.arena, nid_off_ + 2 * node_bound_, nb),
                            adjs, range, y, x, owners, y_flat);
     }
@@ -352,6 +375,8 @@ class HostSession {
   py::object error_cls_;
   std::deque<Slot> slots_;  // stable addresses
   std::deque<Slot*> free_, pending_;
+  bool y_separate_ = false;  // labels are not int64: their own window behind x instead of the arena's tail
+  int64_t x_byte_off_ = 0, y_byte_off_ = 0, block_bytes_ = 8;
   int64_t total_ = 0, next_ = 0, consumed_ = 0, blocked_us_ = 0, blocked_occasions_ = 0;
 };
 
@@ -371,6 +396,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_property_readonly("issued", &HostSession::issued)
       .def_property_readonly("total", &HostSession::total)
       .def_property_readonly("in_flight", &HostSession::in_flight)
+      .def_property_readonly("block_bytes", &HostSession::block_bytes)
       .def_property_readonly("blocked_us", &HostSession::blocked_us)
       .def_property_readonly("blocked_occasions", &HostSession::blocked_occasions);
 }

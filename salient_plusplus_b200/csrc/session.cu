@@ -304,6 +304,15 @@ static double now_s() {
 }
 
 constexpr int kRing = 256;  // tickets in flight (a Session keeps <= 8)
+constexpr int kSpinIters = 4000;  // ~100 us of pause instructions before the worker sleeps
+
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield" ::: "memory");
+#endif
+}
 
 struct Executor {
   int device;
@@ -311,6 +320,7 @@ struct Executor {
   std::mutex mu;
   std::condition_variable cv_work, cv_done;
   std::deque<std::pair<uint64_t, spp_batch_job>> queue;
+  std::atomic<uint64_t> submitted{0};  // jobs ever queued (the worker spins on it before it sleeps)
   bool stop = false;
   uint64_t next_ticket = 1;
   uint64_t issued = 0;  // every ticket <= issued has had its CUDA calls issued
@@ -330,14 +340,21 @@ struct Executor {
   void run() {
     cudaSetDevice(device);
     for (int i = 0; i < kRing; ++i) cudaEventCreateWithFlags(&events[i], cudaEventDisableTiming);
+    uint64_t taken = 0;
     while (true) {
       std::pair<uint64_t, spp_batch_job> item;
+      // A Session hands over a job every 30-100 us.  Sleeping on the condition variable between two
+      // jobs costs the submitting (consumer) thread a futex wake and the job a wake-up latency of
+      // several microseconds, so the worker first spins for about that long (~100 us) and only then
+      // sleeps; between Sessions it sleeps.
+      for (int spin = 0; spin < kSpinIters && submitted.load(std::memory_order_acquire) == taken; ++spin) cpu_relax();
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_work.wait(lk, [this] { return stop || !queue.empty(); });
         if (queue.empty()) break;  // stop requested and drained
         item = queue.front();
         queue.pop_front();
+        ++taken;
       }
       const int slot = (int)(item.first % kRing);
       t_begin[slot] = now_s();
@@ -418,8 +435,9 @@ uint64_t spp_executor_submit(void* executor, const spp_batch_job* job) {
     t = ex->next_ticket++;
     ex->t_submit[t % spp::kRing] = spp::now_s();
     ex->queue.emplace_back(t, *job);
+    ex->submitted.fetch_add(1, std::memory_order_release);
   }
-  ex->cv_work.notify_one();
+  ex->cv_work.notify_one();  // no system call unless the worker sleeps
   return t;
 }
 

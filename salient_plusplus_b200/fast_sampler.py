@@ -826,10 +826,15 @@ class Session:
         self._executor = None
         if not self._full and os.environ.get("SPP_EXECUTOR", "1") != "0":
             self._executor = _executor(self._device.index)
+        # The per-batch bookkeeping (output allocation, job fill, submit, view cutting) runs in the
+        # native host path (csrc/host_session.cpp) whenever batches go through the executor;
+        # SPP_NATIVE_HOST=0 keeps the interpreter implementation below (_enqueue / _finalize).
+        use_native = self._executor is not None and os.environ.get("SPP_NATIVE_HOST", "1") != "0"
         if not self._full:
             for s_ in self._slots:
                 self._init_job(s_)
-                self._prime_allocator(s_)
+                if not use_native:
+                    self._prime_allocator(s_)
         self._free = deque(self._slots)
         self._pending: deque = deque()
         self._freq = None
@@ -844,11 +849,10 @@ class Session:
         for s in self._slots:
             s.stream.wait_stream(cur)
         if _t: _t.append(time.perf_counter())
-        # The per-batch bookkeeping (output allocation, job fill, submit, view cutting) runs in the
-        # native host path (csrc/host_session.cpp) whenever batches go through the executor;
-        # SPP_NATIVE_HOST=0 keeps the interpreter implementation below (_enqueue / _finalize).
-        if self._executor is not None and os.environ.get("SPP_NATIVE_HOST", "1") != "0":
+        if use_native:
             self._native = _lib.load_host().HostSession(self._native_spec())
+            for s_ in self._slots:  # the native path allocates ONE block per batch: prime that size
+                self._prime_allocator(s_, block_bytes=int(self._native.block_bytes))
             self._native.fill()
         else:
             while self._free and self._next < self._num_total:
@@ -1048,14 +1052,15 @@ class Session:
             entry_points=(lib.spp_executor_submit, lib.spp_executor_poll, lib.spp_executor_wait, lib.spp_last_error),
             slots=self._slots, e_id=_empty_eid(self._device))
 
-    def _prime_allocator(self, slot: "_Slot", blocks: int = 3):
+    def _prime_allocator(self, slot: "_Slot", blocks: int = 3, block_bytes: Optional[int] = None):
         """Per-batch outputs are allocated at their upper bounds from PyTorch's caching allocator
         on the slot's stream.  A cache miss there is a cudaMalloc of a few hundred MB (2-30 ms,
         measured), so the first time a slot sees a given output size its pool is primed with the
-        blocks a steady-state pipeline needs (in flight + held by the consumer + prefetched)."""
+        blocks a steady-state pipeline needs (in flight + held by the consumer + prefetched).
+        ``block_bytes``: the native host path's single block per batch (arena + x + y)."""
         fdim, fdtype = self._feat_shape
         x_rows = slot.ws.max_nodes if slot.cjob.feature_mode else 0
-        key = (self._lay[3], x_rows, fdim, fdtype)
+        key = ("block", int(block_bytes)) if block_bytes is not None else (self._lay[3], x_rows, fdim, fdtype)
         primed = getattr(slot, "primed", None)
         if primed is None:
             primed = slot.primed = set()
@@ -1065,6 +1070,9 @@ class Session:
         with torch.cuda.stream(slot.stream):
             keep = []
             for _ in range(blocks):
+                if block_bytes is not None:
+                    keep.append(torch.empty(int(block_bytes), dtype=torch.uint8, device=self._device))
+                    continue
                 keep.append(torch.empty(self._lay[3], dtype=torch.int64, device=self._device))
                 if x_rows:
                     keep.append(torch.empty((x_rows, fdim), dtype=fdtype, device=self._device))
