@@ -303,7 +303,11 @@ static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-constexpr int kRing = 256;  // tickets in flight (a Session keeps <= 8)
+// Tickets whose state is kept (ring indexed by ticket number).  A Session keeps <= 8 in flight, but
+// several Sessions share a device's executor -- a training iterator can sit on its pending batches
+// while an evaluation pass consumes thousands through the same executor -- so the ring is sized for
+// 65 536 newer tickets before an unconsumed one expires; its events are created on first use.
+constexpr int kRing = 1 << 16;
 constexpr int kSpinIters = 4000;  // ~100 us of pause instructions before the worker sleeps
 
 static inline void cpu_relax() {
@@ -339,7 +343,6 @@ struct Executor {
 
   void run() {
     cudaSetDevice(device);
-    for (int i = 0; i < kRing; ++i) cudaEventCreateWithFlags(&events[i], cudaEventDisableTiming);
     uint64_t taken = 0;
     while (true) {
       std::pair<uint64_t, spp_batch_job> item;
@@ -361,7 +364,9 @@ struct Executor {
       int rc = spp_batch_enqueue(&item.second);
       std::string err;
       if (rc != 0) err = spp_last_error();
-      cudaError_t e = cudaEventRecord(events[slot], (cudaStream_t)item.second.stream);
+      cudaError_t e = cudaSuccess;
+      if (!events[slot]) e = cudaEventCreateWithFlags(&events[slot], cudaEventDisableTiming);  // first lap of the ring
+      if (e == cudaSuccess) e = cudaEventRecord(events[slot], (cudaStream_t)item.second.stream);
       t_end[slot] = now_s();
       if (rc == 0 && e != cudaSuccess) {
         rc = (int)e;

@@ -8,7 +8,7 @@ mkdir -p $O
 echo "pytest rc=$?" >> $O/r02_tests_host_g1.log
 tail -6 $O/r02_tests_host_g1.log
 for w in arxiv products-layerwise; do
-  for nat in 1 0; do
+  for nat in 1; do
     SPP_NATIVE_HOST=$nat timeout 120 python bench.py --workload $w --steps 400 --warmup 20 --no-cpu-baseline \
       > $O/r02_host_${w}_native${nat}.json 2> $O/r02_host_${w}_native${nat}.err
     echo "== $w native=$nat rc=$?"; python - <<P
