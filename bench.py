@@ -990,6 +990,11 @@ def layerwise(args):
     barrier()
     # e2e: seeds in (pinned) host memory, H2D per batch + D2H of the size block
     t_e2e, _, nodes_e, _, lat, first_us, it = timed_loop(idx_host)
+    try:  # time the consumer spent waiting for a batch that was not ready (GPU-bound share of the loop)
+        st_ = it.it.get_stats()
+        blocked_us, blocked_n = round(st_.total_blocked_dur.total_seconds() * 1e6, 1), int(st_.total_blocked_occasions)
+    except Exception:  # noqa: BLE001
+        blocked_us, blocked_n = None, None
     clk = clocks.stop()
     lat.sort()
     if world > 1:
@@ -1047,7 +1052,8 @@ def layerwise(args):
                     "gathered_GBps": round(world * nodes_e * row_bytes / t_e2e / 1e9, 2), "api": "FastSampler -> DevicePrefetcher",
                     "timing": f"one iterator over {W}+{K} batches, clock from the delivery of warm-up batch {W}",
                     "per_batch_us": {"p50": round(lat[len(lat) // 2] * 1e6, 1), "p90": round(lat[int(len(lat) * 0.9)] * 1e6, 1),
-                                     "max": round(lat[-1] * 1e6, 1), "first_batch_after_iter_creation": round(first_us, 1)}},
+                                     "max": round(lat[-1] * 1e6, 1), "first_batch_after_iter_creation": round(first_us, 1),
+                                     "consumer_blocked_us_total": blocked_us, "consumer_blocked_batches": blocked_n}},
             "gpu_launches": launches, "clocks": clk,
             "kernel_ms": {k_: round(v, 5) for k_, v in sorted(k_ms.items())},
             "value_loop_diagnostics": diag,

@@ -55,20 +55,23 @@ struct Slot {
   int64_t start = 0, stop = 0;
 };
 
-// A contiguous window of `base`'s storage as a tensor of its own: `sizes` elements (row-major, at most
-// four dimensions) starting `offset` elements into the view `base`.  Built the way ATen's own
-// alias_with_sizes_and_strides builds a view -- a TensorImpl on the shared Storage -- instead of
-// through narrow()/view() and the dispatcher: a batch is cut into 8-20 such windows and each dispatched
-// view op costs microseconds of host time, which is the whole budget on the small graph shapes.
-at::Tensor window(const at::Tensor& base, int64_t offset, c10::IntArrayRef sizes) {
-  auto t = at::detail::make_tensor<c10::TensorImpl>(c10::TensorImpl::VIEW, c10::Storage(base.storage()), base.key_set(),
-                                                    base.dtype());
+// `sizes` elements (row-major, at most four dimensions) of `owner`'s storage as a tensor of its own,
+// starting `element_offset` elements of type `dtype` into the storage.  Built the way ATen's own
+// alias_with_sizes_and_strides builds a view -- a TensorImpl on the shared Storage -- instead of through
+// narrow() / view() and the dispatcher: a batch is cut into 8-20 such windows and each dispatched view
+// op costs microseconds of host time, which is the whole budget on the small graph shapes.
+at::Tensor storage_window(const at::Tensor& owner, caffe2::TypeMeta dtype, int64_t element_offset, c10::IntArrayRef sizes) {
+  auto t = at::detail::make_tensor<c10::TensorImpl>(c10::TensorImpl::VIEW, c10::Storage(owner.storage()), owner.key_set(), dtype);
   auto* impl = t.unsafeGetTensorImpl();
-  impl->set_storage_offset(base.storage_offset() + offset);
+  impl->set_storage_offset(element_offset);
   int64_t strides[4] = {1, 1, 1, 1};
   for (int d = (int)sizes.size() - 2; d >= 0; --d) strides[d] = strides[d + 1] * std::max<int64_t>(sizes[d + 1], 1);
   impl->set_sizes_and_strides(sizes, c10::IntArrayRef(strides, sizes.size()));
   return t;
+}
+// a window of the view `base`, `offset` of its elements in
+at::Tensor window(const at::Tensor& base, int64_t offset, c10::IntArrayRef sizes) {
+  return storage_window(base, base.dtype(), base.storage_offset() + offset, sizes);
 }
 at::Tensor window(const at::Tensor& base, int64_t offset, int64_t rows) {
   return window(base, offset, c10::IntArrayRef(&rows, 1));
@@ -77,17 +80,10 @@ at::Tensor window(const at::Tensor& base, int64_t offset, int64_t rows, int64_t 
   const int64_t sizes[2] = {rows, cols};
   return window(base, offset, c10::IntArrayRef(sizes, 2));
 }
-
-// Same, for a window of another element type: `byte_offset` bytes into the byte block `block`.
+// a window of another element type, `byte_offset` bytes into the byte block `block`
 at::Tensor typed_window(const at::Tensor& block, int64_t byte_offset, at::ScalarType dtype, c10::IntArrayRef sizes) {
-  auto t = at::detail::make_tensor<c10::TensorImpl>(c10::TensorImpl::VIEW, c10::Storage(block.storage()), block.key_set(),
-                                                    c10::scalarTypeToTypeMeta(dtype));
-  auto* impl = t.unsafeGetTensorImpl();
-  impl->set_storage_offset((block.storage_offset() + byte_offset) / (int64_t)c10::elementSize(dtype));
-  int64_t strides[4] = {1, 1, 1, 1};
-  for (int d = (int)sizes.size() - 2; d >= 0; --d) strides[d] = strides[d + 1] * std::max<int64_t>(sizes[d + 1], 1);
-  impl->set_sizes_and_strides(sizes, c10::IntArrayRef(strides, sizes.size()));
-  return t;
+  return storage_window(block, c10::scalarTypeToTypeMeta(dtype),
+                        (block.storage_offset() + byte_offset) / (int64_t)c10::elementSize(dtype), sizes);
 }
 
 inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }

@@ -418,6 +418,43 @@ def test_plain_launches_match_graph_replay():
     assert " passed" in r.stdout
 
 
+def test_native_host_path_is_default_and_matches_interpreter(fs, data, monkeypatch):
+    """Sessions whose batches go through the executor run their per-batch bookkeeping in the native
+    host path (csrc/host_session.cpp); SPP_NATIVE_HOST=0 selects the interpreter implementation.
+    Same batches bit for bit (sampling is a pure function of the seeds and the per-batch key), one
+    block per batch as the owner of every tensor on the native side."""
+    rowptr, col, x, y, N = data
+    idx = S.seeds(N, 300)
+
+    def drain(native):
+        if native:
+            monkeypatch.delenv("SPP_NATIVE_HOST", raising=False)
+        else:
+            monkeypatch.setenv("SPP_NATIVE_HOST", "0")
+        sess = fs.Session(4, 3, _config(fs, x, y, rowptr, col, idx))
+        assert (sess._native is not None) == native
+        out = []
+        while True:
+            b = sess.blocking_get_batch()
+            if b is None:
+                break
+            if native:
+                assert len(b.owners) == 1 and b.owners[0].dtype == torch.uint8
+                assert b.y_flat is not None and b.y_flat.shape == b[1].squeeze().shape
+                base = b.owners[0].untyped_storage().data_ptr()
+                assert all(t.untyped_storage().data_ptr() == base for t in (b[0], b[1], b[2][0][0], b[2][0][1]))
+            out.append((b[3], b[0].cpu(), b[1].cpu(), [(a[0].cpu(), a[1].cpu(), a[3]) for a in b[2]]))
+        assert sess.num_consumed_batches == sess.num_total_batches
+        return out
+
+    nat, ref = drain(True), drain(False)
+    assert len(nat) == len(ref) == 5
+    for (r1, x1, y1, a1), (r2, x2, y2, a2) in zip(nat, ref):
+        assert r1 == r2 and torch.equal(x1, x2) and torch.equal(y1, y2)
+        for (p1, c1, s1), (p2, c2, s2) in zip(a1, a2):
+            assert torch.equal(p1, p2) and torch.equal(c1, c2) and tuple(s1) == tuple(s2)
+
+
 def test_tunables_reject_unknown_keys():
     from salient_plusplus_b200 import _lib
     with pytest.raises(_lib.SalientB200Error):
