@@ -304,3 +304,59 @@ def test_spec_validation(fx, host):
         host.HostSession(fs.host_session_spec(**dict(base, idx_dev_ptr=8, batch_edges=[1, 2])))
     with pytest.raises((ValueError, RuntimeError)):        # one (rowptr, col) offset pair per hop
         host.HostSession(fs.host_session_spec(**dict(base, idx_dev_ptr=8, n_hops=2)))
+
+
+def test_randomized_sweep(fx, host):
+    """Seeded sweep over hop counts, partition counts, batch / slot / seed counts, label dtypes, seed
+    residency and readiness patterns: every delivered piece is compared with the stand-in's pattern,
+    mixing try / blocking getters the way a consumer does."""
+    import random
+    rnd = random.Random(20261018)
+    for trial in range(40):
+        L = rnd.choice([1, 2, 3, 4])
+        P = rnd.choice([-1, -1, 1, 2, 5, 16])
+        bs = rnd.choice([1, 3, 16, 33])
+        n_seeds = rnd.randint(1, 6 * bs + 2)
+        depth = rnd.choice([1, 2, 6])
+        polls = rnd.choice([0, 0, 1, 3])
+        y_dtype = rnd.choice([torch.int64, torch.int32, torch.float32])
+        on_dev = rnd.random() < 0.5
+        feat = rnd.random() < 0.8
+        hs, ex, ranges, idx, (caps, keep) = make(fx, host, n_seeds=n_seeds, bs=bs, L=L, P=P, depth=depth, polls=polls,
+                                                  y_dtype=y_dtype, idx_on_device=on_dev, feat=feat)
+        hs.fill()
+        assert hs.total == len(ranges) and hs.in_flight == min(depth, len(ranges))
+        got = 0
+        while got < len(ranges):
+            r = hs.get(rnd.random() < 0.7)
+            if r is None:
+                continue                      # try-get on a batch that is not ready yet
+            st, en = ranges[got]
+            seed0 = int(idx[st])
+            if P < 0:
+                x, y, adjs, rng, owners, y_flat = r
+                n_id = None
+            else:
+                n_id, parts, cached, perm, adjs, rng, y, x, owners, y_flat = r
+            assert rng == (st, en)
+            nb = check_structure(adjs, seed0, en - st, caps)
+            if feat:
+                assert x.shape == (nb, 8) and x.view(torch.uint8)[:, 0].tolist() == [(seed0 + i) & 0xff for i in range(nb)]
+            elif P < 0:
+                assert x.shape == (0, 8)
+            else:
+                assert x is None
+            assert y.shape == (en - st, 1) and y.dtype == y_dtype
+            assert y_flat.shape == y.squeeze().shape and y_flat.data_ptr() == y.data_ptr() and y_flat.dtype == y_dtype
+            if y_dtype == torch.int64:       # the stand-in only writes 8-byte labels
+                assert y.view(-1).tolist() == (3 * idx[st:en]).tolist()
+            if P >= 0:
+                assert n_id.tolist() == [seed0 + i for i in range(nb)] and perm.tolist() == [nb - 1 - i for i in range(nb)]
+                assert [p.numel() for p in parts] == [nb // (P + 1)] * P and cached.numel() == nb - P * (nb // (P + 1))
+                assert torch.cat(list(parts) + [cached]).tolist() == [7 * pos + seed0 for pos in range(nb)]
+                assert inside(owners, n_id, cached, perm, y, *parts)
+            assert inside(owners, y, *[t for a in adjs for t in a[:2]]) and (x is None or inside(owners, x))
+            got += 1
+        assert hs.get(True) is None and hs.consumed == hs.total and fx.fx_submitted(ex) == len(ranges)
+        del hs
+        fx.fx_destroy(ex)
