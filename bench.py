@@ -150,9 +150,19 @@ def log(msg):
 _T0 = time.perf_counter()
 
 
+FEAT_DTYPE = None   # --feat-dtype: overrides the shape's feature dtype ("products ... also report fp32")
+
+
+def ref_threads(args) -> int:
+    """Worker threads of the CPU reference legs: every host core, or --ref-threads (the reference's
+    launcher default is 15 workers per GPU, utils/exp_driver.py:48)."""
+    return int(args.ref_threads) if getattr(args, "ref_threads", 0) else (os.cpu_count() or 1)
+
+
 def make_graph(shape: str, scale: float, device, locality: float = 0.0, parts: int = 8):
     from salient_plusplus_b200 import synthetic as S
     n, e, f, dt = S.SHAPES[shape]
+    dt = FEAT_DTYPE or dt
     if shape in ("papers100M", "mag240m"):
         e //= 2  # BASELINE's 1.6B is taken as the CSR entry count (SURVEY.md 8d: "say which")
     n, e = max(1024, int(n * scale)), max(4096, int(e * scale))
@@ -313,13 +323,15 @@ def reference_arm(args):
     from salient_plusplus_b200 import synthetic as S
     from salient_plusplus_b200.peer import hosted_partitions
     shape, sizes, bs, _, desc = WORKLOADS[args.workload]
+    if args.feat_dtype != "default":
+        desc += f" [features stored as {args.feat_dtype} for this run]"
     N = max(args.gpus, 1)
     P = num_parts(args, N)
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     n, f, dt, rowptr, col = make_graph(shape, args.scale, dev, args.locality, max(P, 1))
     deg = (rowptr[1:] - rowptr[:-1]) if N > 1 else None
     rowptr, col = rowptr.cpu(), col.cpu()
-    threads = os.cpu_count() or 1
+    threads = ref_threads(args)
     W, K = args.warmup, args.steps
     layerwise = args.workload == "products-layerwise"
     if N == 1 or layerwise:
@@ -460,6 +472,8 @@ def ours(args):
     lib = _lib.load()
 
     shape, sizes, bs, _, desc = WORKLOADS[args.workload]
+    if args.feat_dtype != "default":
+        desc += f" [features stored as {args.feat_dtype} for this run]"
     K, W = args.steps, args.warmup
     P = num_parts(args, world)
     n, f, dt, rowptr, col = make_graph(shape, args.scale, dev, args.locality, max(P, 1))
@@ -633,7 +647,7 @@ def ours(args):
     peak, peak_src = measured_peaks()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r02_gather_traffic.json")
-    if os.path.exists(tp) and world == 1:
+    if os.path.exists(tp) and world == 1 and args.feat_dtype == "default":
         try:  # ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum per launch) of the same workload
             traffic = json.load(open(tp)).get(f"{args.workload}_p{P}")
         except Exception:  # noqa: BLE001
@@ -775,7 +789,7 @@ def ours(args):
     cpu = None
     oracle_check = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = ref_threads(args)
         cb = max(96, 10 * threads)   # >= 10 waves of the thread pool, bounded by max_seconds below
         pre = 2 * threads
         rp_h, col_h = rowptr.cpu(), col32.to(torch.int64).cpu()
@@ -1005,7 +1019,7 @@ def layerwise(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import numpy as np
         from oracle import oracle as O
-        threads = os.cpu_count() or 1
+        threads = ref_threads(args)
         rp_h, col_h = rowptr.cpu(), col32.to(torch.int64).cpu()
         good = True
         for q in range(3):   # whole batches, bit for bit (deterministic path)
@@ -1100,8 +1114,16 @@ def main():
     ap.add_argument("--device-only", action="store_true",
                     help="A/B experiments: print the device-timed batches/s and exit (not a bench line)")
     ap.add_argument("--profile-e2e", action="store_true", help="cProfile the public-API loop (stderr)")
+    ap.add_argument("--feat-dtype", default="default", choices=["default", "fp16", "fp32"],
+                    help="feature dtype of the synthetic table (default: the shape's own; the reference stores "
+                         "ogbn-products as fp16, driver/dataset.py:70)")
+    ap.add_argument("--ref-threads", type=int, default=0,
+                    help="worker threads of the CPU reference (cpu_baseline leg and --impl reference); 0 = every host "
+                         "core, 15 = the reference launcher's default per GPU (utils/exp_driver.py:48)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global FEAT_DTYPE
+    FEAT_DTYPE = {"default": None, "fp16": torch.float16, "fp32": torch.float32}[args.feat_dtype]
     if args.impl == "reference":
         reference_arm(args)
     elif args.workload == "products-layerwise":
